@@ -1,0 +1,1173 @@
+// cobs_b200/csrc/cobsgpu.cu -- implementation of the C ABI declared in include/cobsgpu.h.
+//
+// Host orchestration of the three kernels (K1 hash.cuh, K2 score.cuh, K3 select.cuh) that
+// replace cobs::ClassicSearch::search (cobs/query/classic_search.cpp:403-505) for one index,
+// plus the loader that lays the signature matrix out in HBM.  No CPU compute path exists:
+// without a usable CUDA device every entry point fails with COBSGPU_ERR_CUDA.
+//
+// HBM layout: every (local) page is a row-major matrix [signature_size][pitch] bytes, pitch =
+// row bytes rounded up to 128 (16 for rows < 512 B) and zero padded, so each row slice a tile
+// needs is one aligned contiguous run that a single cp.async.bulk can fetch.  Bit d of a row
+// = byte d/8, bit d%8 (LSB first), exactly the reference's file layout
+// (cobs/construction/classic_index.cpp:40-43).
+#include "../../include/cobsgpu.h"
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "fill.cuh"
+#include "hash.cuh"
+#include "index_file.hpp"
+#include "score.cuh"
+#include "select.cuh"
+
+using namespace cobsgpu;
+
+namespace {
+
+struct Err {
+    int code;
+    std::string msg;
+};
+
+thread_local std::string g_error;
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            throw Err{ e_ == cudaErrorMemoryAllocation ? COBSGPU_ERR_OOM : COBSGPU_ERR_CUDA, \
+                       std::string(#call) + ": " + cudaGetErrorString(e_) };              \
+    } while (0)
+
+template <typename F>
+int guarded(F&& f) {
+    try {
+        f();
+        return COBSGPU_OK;
+    }
+    catch (const Err& e) {
+        g_error = e.msg;
+        return e.code;
+    }
+    catch (const std::bad_alloc&) {
+        g_error = "host out of memory";
+        return COBSGPU_ERR_OOM;
+    }
+    catch (const std::exception& e) {
+        g_error = e.what();
+        return COBSGPU_ERR_INVALID_ARG;
+    }
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t n) {
+        if (n <= cap) return;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        n = round_up<size_t>(n + n / 4, 256);
+        CK(cudaMalloc(&p, n));
+        cap = n;
+    }
+    template <typename T>
+    T* as() const {
+        return static_cast<T*>(p);
+    }
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t n) {
+        if (n <= cap) return;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        n = round_up<size_t>(n + n / 4, 256);
+        CK(cudaMallocHost(&p, n));
+        cap = n;
+    }
+    template <typename T>
+    T* as() const {
+        return static_cast<T*>(p);
+    }
+    ~PinBuf() {
+        if (p) cudaFreeHost(p);
+    }
+};
+
+struct LocalPage {
+    uint32_t global_page;
+    uint64_t sig;
+    uint32_t pitch;
+    uint32_t row_bytes;     // source-row bytes held by this shard
+    uint32_t rb16;          // row_bytes rounded up to 16 (what the tiles cover)
+    uint64_t byte_begin;    // first source-row byte held
+    uint32_t doc_base;      // global document id of bit 0
+    uint32_t n_real;        // real documents among the 8*row_bytes columns held
+    uint32_t dense_off;     // first column in the shard-local dense layout
+    uint8_t* d_base;
+};
+
+enum Phase { PH_H2D = 0, PH_HASH, PH_SCORE, PH_SELECT, PH_D2H, PH_COUNT };
+
+}  // namespace
+
+struct cobsgpu_index {
+    // description
+    int kind = 0;
+    uint32_t term_size = 0, canonicalize = 0, num_hashes = 0, n_docs = 0, n_pages_global = 0;
+    uint64_t page_size_src = 0;   // bytes per row per page in the source layout
+    int device = 0;
+    uint32_t shard_index = 0, shard_count = 1;
+    std::vector<std::string> doc_names;
+    std::unique_ptr<IndexFile> file;
+
+    // HBM layout
+    std::vector<LocalPage> pages;
+    uint8_t* d_arena = nullptr;
+    uint64_t hbm_bytes = 0;
+    uint32_t ncw = 1;             // consumer warps per CTA -> tile width 512*ncw
+    std::vector<TileDesc> tiles;
+    TileDesc* d_tiles = nullptr;
+    uint64_t dense_pitch = 128;
+    uint32_t shard_real_docs = 0;
+    uint32_t shard_doc_begin = 0, shard_doc_end = 0;
+    uint64_t bytes_per_kmer = 0;
+    uint32_t* d_seg = nullptr;    // [3][n_local_pages]: dense_off, n_real, doc_base
+
+    // device properties
+    int sm_count = 0;
+    size_t smem_optin = 0;
+
+    // options
+    uint32_t max_candidates = 1024;
+    uint32_t max_batch = 16384;
+    uint64_t workspace_bytes = 1024ull << 20;
+    bool timing = false;
+
+    // execution state
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    DevBuf d_queries, d_qoff, d_koff, d_thr, d_hashes, d_flags, d_qlist;
+    DevBuf d_cand, d_scratch, d_cand_count, d_res_count, d_offsets, d_out_doc, d_out_score, d_dense;
+    PinBuf h_stage, h_off, h_doc, h_score, h_counts, h_dense;
+    // current batch (host copies)
+    std::vector<uint64_t> b_qoff;
+    std::vector<uint32_t> b_koff, b_thr;
+    uint32_t b_nq = 0, b_total_kmers = 0;
+    const char* b_dev_queries = nullptr;
+
+    // results of the last search_batch call
+    std::vector<uint64_t> r_off;
+    std::vector<uint32_t> r_doc, r_score;
+
+    // timers
+    cobsgpu_timers tm{};
+    struct Ev {
+        cudaEvent_t a, b;
+        int phase;
+    };
+    std::vector<Ev> pending;
+    std::vector<cudaEvent_t> ev_pool;
+
+    ~cobsgpu_index() {
+        cudaSetDevice(device);
+        for (auto& e : pending) {
+            cudaEventDestroy(e.a);
+            cudaEventDestroy(e.b);
+        }
+        for (auto e : ev_pool) cudaEventDestroy(e);
+        if (d_arena) cudaFree(d_arena);
+        if (d_tiles) cudaFree(d_tiles);
+        if (d_seg) cudaFree(d_seg);
+        if (own_stream && stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------------------
+// phase timing with CUDA events (only when the "timing" option is on)
+
+struct PhaseScope {
+    cobsgpu_index* ix;
+    cudaEvent_t a = nullptr, b = nullptr;
+    int phase;
+    cudaStream_t st;
+    PhaseScope(cobsgpu_index* ix_, int phase_, cudaStream_t st_) : ix(ix_), phase(phase_), st(st_) {
+        if (!ix->timing) return;
+        a = take();
+        b = take();
+        cudaEventRecord(a, st);
+    }
+    cudaEvent_t take() {
+        if (!ix->ev_pool.empty()) {
+            cudaEvent_t e = ix->ev_pool.back();
+            ix->ev_pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+    ~PhaseScope() {
+        if (!ix->timing) return;
+        cudaEventRecord(b, st);
+        ix->pending.push_back({ a, b, phase });
+    }
+};
+
+void resolve_timers(cobsgpu_index* ix) {
+    for (auto& e : ix->pending) {
+        float ms = 0;
+        if (cudaEventSynchronize(e.b) == cudaSuccess && cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) {
+            switch (e.phase) {
+            case PH_H2D: ix->tm.h2d_ms += ms; break;
+            case PH_HASH: ix->tm.hashes_ms += ms; break;
+            case PH_SCORE: ix->tm.score_ms += ms; break;
+            case PH_SELECT: ix->tm.select_ms += ms; break;
+            case PH_D2H: ix->tm.d2h_ms += ms; break;
+            }
+        }
+        ix->ev_pool.push_back(e.a);
+        ix->ev_pool.push_back(e.b);
+    }
+    ix->pending.clear();
+}
+
+// ---------------------------------------------------------------------------------------
+// index layout
+
+void check_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        throw Err{ COBSGPU_ERR_CUDA,
+                   std::string("no CUDA device available (libcobsgpu has no CPU fallback): ") +
+                       cudaGetErrorString(e) };
+    if (device < 0 || device >= n)
+        throw Err{ COBSGPU_ERR_INVALID_ARG, "device ordinal out of range" };
+    CK(cudaSetDevice(device));
+}
+
+void build_layout(cobsgpu_index* ix, const std::vector<uint64_t>& sig) {
+    const uint32_t P = ix->n_pages_global;
+    const uint64_t ps = ix->page_size_src;
+    const uint32_t S = ix->shard_count, g = ix->shard_index;
+    ix->pages.clear();
+    if (ix->kind == COBSGPU_KIND_CLASSIC) {
+        // contiguous column ranges cut at multiples of 128 documents (16 bytes)
+        const uint64_t gran = div_ceil<uint64_t>(ps, 16);
+        const uint64_t lo = gran * g / S, hi = gran * (g + 1) / S;
+        const uint64_t b0 = lo * 16, b1 = std::min<uint64_t>(hi * 16, ps);
+        if (b1 > b0) {
+            LocalPage lp{};
+            lp.global_page = 0;
+            lp.sig = sig[0];
+            lp.byte_begin = b0;
+            lp.row_bytes = static_cast<uint32_t>(b1 - b0);
+            lp.doc_base = static_cast<uint32_t>(8 * b0);
+            ix->pages.push_back(lp);
+        }
+    } else {
+        // whole pages per shard, contiguous ranges balanced by bytes
+        long double total = 0;
+        for (uint32_t p = 0; p < P; ++p) total += static_cast<long double>(sig[p]) * ps;
+        long double cum = 0;
+        for (uint32_t p = 0; p < P; ++p) {
+            const long double sz = static_cast<long double>(sig[p]) * ps;
+            uint32_t owner = total > 0 ? static_cast<uint32_t>((cum + sz / 2) * S / total) : 0;
+            if (owner >= S) owner = S - 1;
+            cum += sz;
+            if (owner != g) continue;
+            LocalPage lp{};
+            lp.global_page = p;
+            lp.sig = sig[p];
+            lp.byte_begin = 0;
+            lp.row_bytes = static_cast<uint32_t>(ps);
+            lp.doc_base = static_cast<uint32_t>(static_cast<uint64_t>(p) * 8 * ps);
+            ix->pages.push_back(lp);
+        }
+    }
+    uint32_t max_rb16 = 16;
+    uint64_t dense = 0, arena = 0;
+    ix->shard_real_docs = 0;
+    ix->bytes_per_kmer = 0;
+    ix->shard_doc_begin = ix->pages.empty() ? 0 : ix->pages.front().doc_base;
+    ix->shard_doc_end = ix->shard_doc_begin;
+    for (auto& lp : ix->pages) {
+        lp.rb16 = round_up<uint32_t>(lp.row_bytes, 16);
+        lp.pitch = lp.row_bytes >= 512 ? round_up<uint32_t>(lp.row_bytes, 128) : lp.rb16;
+        const uint64_t cols = static_cast<uint64_t>(lp.row_bytes) * 8;
+        lp.n_real = ix->n_docs > lp.doc_base
+                        ? static_cast<uint32_t>(std::min<uint64_t>(ix->n_docs - lp.doc_base, cols))
+                        : 0;
+        if (dense + static_cast<uint64_t>(lp.rb16) * 8 > 0xFFFFFF00ull)
+            throw Err{ COBSGPU_ERR_INVALID_ARG, "shard holds more than 2^32 columns" };
+        lp.dense_off = static_cast<uint32_t>(dense);
+        dense += static_cast<uint64_t>(lp.rb16) * 8;
+        arena += round_up<uint64_t>(lp.sig * lp.pitch, 256);
+        max_rb16 = std::max(max_rb16, lp.rb16);
+        ix->shard_real_docs += lp.n_real;
+        ix->bytes_per_kmer += static_cast<uint64_t>(ix->num_hashes) * lp.row_bytes;
+        ix->shard_doc_end = lp.doc_base + static_cast<uint32_t>(cols);
+    }
+    ix->dense_pitch = std::max<uint64_t>(128, round_up<uint64_t>(dense, 128));
+    ix->ncw = std::min<uint32_t>(4, std::max<uint32_t>(1, div_ceil<uint32_t>(max_rb16, 512)));
+    ix->hbm_bytes = arena;
+}
+
+void build_tiles(cobsgpu_index* ix) {
+    const uint32_t W = ix->ncw * 512;
+    ix->tiles.clear();
+    for (auto& lp : ix->pages) {
+        const uint32_t n = div_ceil<uint32_t>(lp.rb16, W);
+        // even split; 128-byte aligned tile width when that still fits in W
+        uint32_t tb = round_up<uint32_t>(div_ceil<uint32_t>(lp.rb16, n), 128);
+        if (tb > W) tb = round_up<uint32_t>(div_ceil<uint32_t>(lp.rb16, n), 16);
+        for (uint32_t off = 0; off < lp.rb16; off += tb) {
+            TileDesc t{};
+            t.base = lp.d_base + off;
+            t.sig = lp.sig;
+            t.pitch = lp.pitch;
+            t.bytes = std::min<uint32_t>(tb, lp.rb16 - off);
+            t.doc_base = lp.doc_base + off * 8;
+            const uint64_t cols = static_cast<uint64_t>(t.bytes) * 8;
+            t.n_real = ix->n_docs > t.doc_base
+                           ? static_cast<uint32_t>(std::min<uint64_t>(ix->n_docs - t.doc_base, cols))
+                           : 0;
+            // columns beyond the real row bytes (16-byte padding) are never real
+            const uint64_t held = static_cast<uint64_t>(lp.row_bytes) * 8;
+            const uint64_t first = static_cast<uint64_t>(off) * 8;
+            const uint64_t in_row = held > first ? std::min<uint64_t>(held - first, cols) : 0;
+            t.n_real = static_cast<uint32_t>(std::min<uint64_t>(t.n_real, in_row));
+            t.dense_off = lp.dense_off + off * 8;
+            ix->tiles.push_back(t);
+        }
+    }
+    if (!ix->tiles.empty()) {
+        CK(cudaMalloc(&ix->d_tiles, ix->tiles.size() * sizeof(TileDesc)));
+        CK(cudaMemcpy(ix->d_tiles, ix->tiles.data(), ix->tiles.size() * sizeof(TileDesc),
+                      cudaMemcpyHostToDevice));
+    }
+    const size_t np = ix->pages.size();
+    if (np) {
+        std::vector<uint32_t> seg(3 * np);
+        for (size_t i = 0; i < np; ++i) {
+            seg[i] = ix->pages[i].dense_off;
+            seg[np + i] = ix->pages[i].n_real;
+            seg[2 * np + i] = ix->pages[i].doc_base;
+        }
+        CK(cudaMalloc(&ix->d_seg, seg.size() * 4));
+        CK(cudaMemcpy(ix->d_seg, seg.data(), seg.size() * 4, cudaMemcpyHostToDevice));
+    }
+}
+
+void open_common(cobsgpu_index* ix, const std::vector<uint64_t>& sig,
+                 const uint8_t* const* page_data, uint64_t fill_seed) {
+    check_device(ix->device);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, ix->device));
+    if (prop.major < 9)
+        throw Err{ COBSGPU_ERR_CUDA, "device lacks bulk-copy/mbarrier support (need sm_100)" };
+    ix->sm_count = prop.multiProcessorCount;
+    ix->smem_optin = prop.sharedMemPerBlockOptin;
+    if (ix->num_hashes == 0 || ix->num_hashes > 32)
+        throw Err{ COBSGPU_ERR_INVALID_ARG, "num_hashes must be in 1..32" };
+    if (ix->term_size == 0) throw Err{ COBSGPU_ERR_INVALID_ARG, "term_size must be > 0" };
+    if (ix->canonicalize > 1)
+        throw Err{ COBSGPU_ERR_INVALID_ARG,
+                   "Unknown canonicalize value " + std::to_string(ix->canonicalize) };
+    if (ix->shard_count == 0 || ix->shard_index >= ix->shard_count)
+        throw Err{ COBSGPU_ERR_INVALID_ARG, "bad shard spec" };
+    for (uint64_t s : sig)
+        if (s == 0) throw Err{ COBSGPU_ERR_INVALID_ARG, "signature_size must be > 0" };
+
+    build_layout(ix, sig);
+    CK(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    ix->own_stream = true;
+    if (ix->hbm_bytes) {
+        CK(cudaMalloc(reinterpret_cast<void**>(&ix->d_arena), ix->hbm_bytes));
+        uint64_t off = 0;
+        for (auto& lp : ix->pages) {
+            lp.d_base = ix->d_arena + off;
+            off += round_up<uint64_t>(lp.sig * lp.pitch, 256);
+        }
+        for (auto& lp : ix->pages) {
+            if (page_data) {
+                // re-pitch while copying: source row stride page_size -> device pitch
+                CK(cudaMemsetAsync(lp.d_base, 0, lp.sig * lp.pitch, ix->stream));
+                const uint8_t* src = page_data[lp.global_page] + lp.byte_begin;
+                const uint64_t chunk = std::max<uint64_t>(1, (256ull << 20) / std::max<uint64_t>(1, ix->page_size_src));
+                for (uint64_t r = 0; r < lp.sig; r += chunk) {
+                    const uint64_t nr = std::min<uint64_t>(chunk, lp.sig - r);
+                    CK(cudaMemcpy2DAsync(lp.d_base + r * lp.pitch, lp.pitch,
+                                         src + r * ix->page_size_src, ix->page_size_src,
+                                         lp.row_bytes, nr, cudaMemcpyHostToDevice, ix->stream));
+                }
+            } else {
+                FillParams fp{ lp.d_base, lp.sig, lp.pitch, lp.row_bytes, lp.byte_begin, fill_seed,
+                               lp.global_page };
+                const uint32_t grid = static_cast<uint32_t>(
+                    std::min<uint64_t>(lp.sig, static_cast<uint64_t>(ix->sm_count) * 16));
+                fill_page_kernel<<<grid, 256, 0, ix->stream>>>(fp);
+                CK(cudaGetLastError());
+            }
+        }
+        CK(cudaStreamSynchronize(ix->stream));
+    }
+    build_tiles(ix);
+}
+
+// ---------------------------------------------------------------------------------------
+// score kernel dispatch
+
+using ScoreFn = void (*)(const ScoreParams);
+
+template <int MODE>
+ScoreFn pick_h(uint32_t h) {
+    switch (h) {
+    case 1: return score_kernel<1, MODE>;
+    case 2: return score_kernel<2, MODE>;
+    case 3: return score_kernel<3, MODE>;
+    case 4: return score_kernel<4, MODE>;
+    default: return score_kernel<0, MODE>;
+    }
+}
+
+ScoreFn pick_score(uint32_t h, int mode) {
+    switch (mode) {
+    case MODE_CAND: return pick_h<MODE_CAND>(h);
+    case MODE_DENSE8: return pick_h<MODE_DENSE8>(h);
+    default: return pick_h<MODE_DENSE32>(h);
+    }
+}
+
+void launch_score(cobsgpu_index* ix, ScoreParams sp, int mode, cudaStream_t st) {
+    if (sp.nq_items == 0 || sp.n_tiles == 0) return;
+    const uint32_t h = ix->num_hashes;
+    const uint32_t W = ix->ncw * 512;
+    const uint32_t stage = h * W;
+    // ring depth from the shared-memory budget: aim for 3 CTAs/SM, fall back to 2 or 1 when
+    // a stage (h row slices) is large
+    const size_t avail = ix->smem_optin;   // 227 KB on B200
+    uint32_t ns = 0;
+    for (int occ = 3; occ >= 1; --occ) {
+        const size_t budget = avail / occ - (occ > 1 ? 1024 : 0);
+        if (budget <= 1024 + stage) continue;
+        ns = static_cast<uint32_t>((budget - 1024) / stage);
+        if (ns >= 4 || occ == 1) break;
+    }
+    if (ns == 0) throw Err{ COBSGPU_ERR_INVALID_ARG, "num_hashes too large for shared memory" };
+    ns = std::min<uint32_t>(ns, 64);
+    sp.n_stages = ns;
+    const size_t smem = round_up<size_t>(ns * 16, 128) + static_cast<size_t>(ns) * stage;
+    ScoreFn fn = pick_score(h, mode);
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const int threads = static_cast<int>((ix->ncw + 1) * 32);
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem));
+    if (occ < 1) throw Err{ COBSGPU_ERR_CUDA, "score kernel does not fit on an SM" };
+    const uint64_t items = static_cast<uint64_t>(sp.nq_items) * sp.n_tiles;
+    const uint32_t grid = static_cast<uint32_t>(
+        std::min<uint64_t>(items, static_cast<uint64_t>(occ) * ix->sm_count));
+    PhaseScope ps(ix, PH_SCORE, st);
+    fn<<<grid, threads, smem, st>>>(sp);
+    CK(cudaGetLastError());
+    ix->tm.kernel_launches++;
+    ix->tm.score_launches++;
+}
+
+// ---------------------------------------------------------------------------------------
+// batch preparation: host geometry, uploads, K1
+
+// flags buffer: [0] first query with an invalid base, [1] first query overflowing its
+// candidate slots
+void reset_flags(cobsgpu_index* ix, cudaStream_t st) {
+    ix->d_flags.ensure(2 * sizeof(int));
+    static const int init[2] = { INT_MAX, INT_MAX };
+    CK(cudaMemcpyAsync(ix->d_flags.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+}
+
+// queries [q0, q1) of the caller's batch; `queries` is a host pointer unless dev_queries
+void prepare_batch(cobsgpu_index* ix, const char* queries, bool dev_queries,
+                   const uint64_t* offsets, uint32_t q0, uint32_t q1, double threshold,
+                   cudaStream_t st) {
+    const uint32_t nq = q1 - q0;
+    const uint32_t k = ix->term_size;
+    ix->b_nq = nq;
+    ix->b_qoff.resize(nq + 1);
+    ix->b_koff.resize(nq + 1);
+    ix->b_thr.resize(nq);
+    const uint64_t base = offsets[q0];
+    uint64_t kmers = 0;
+    for (uint32_t i = 0; i < nq; ++i) {
+        if (offsets[q0 + i + 1] < offsets[q0 + i])
+            throw Err{ COBSGPU_ERR_INVALID_ARG, "query offsets must be non-decreasing" };
+        const uint64_t len = offsets[q0 + i + 1] - offsets[q0 + i];
+        if (len < k)
+            throw Err{ COBSGPU_ERR_QUERY_TOO_SHORT,
+                       "query too short, needs to be at least " + std::to_string(k) +
+                           " characters long (query " + std::to_string(q0 + i) + ")" };
+        const uint64_t T = len - k + 1;
+        if (T >= 0xFFFFFFFFull)
+            throw Err{ COBSGPU_ERR_INVALID_ARG, "query too long" };
+        ix->b_qoff[i] = offsets[q0 + i] - base;
+        ix->b_koff[i] = static_cast<uint32_t>(kmers);
+        kmers += T;
+        // thresholds[i] = ceil(threshold * num_terms) in double (classic_search.cpp:444-449)
+        double th = std::ceil(threshold * static_cast<double>(T));
+        ix->b_thr[i] = th <= 0.0 ? 0u : (th >= 4294967295.0 ? 0xFFFFFFFFu : static_cast<uint32_t>(th));
+    }
+    if (kmers > 0x7FFFFFFFull)
+        throw Err{ COBSGPU_ERR_INVALID_ARG, "batch holds more than 2^31 k-mers" };
+    ix->b_qoff[nq] = offsets[q1] - base;
+    ix->b_koff[nq] = static_cast<uint32_t>(kmers);
+    ix->b_total_kmers = static_cast<uint32_t>(kmers);
+    const uint64_t blob_bytes = ix->b_qoff[nq];
+
+    reset_flags(ix, st);
+    {
+        PhaseScope ps(ix, PH_H2D, st);
+        if (dev_queries) {
+            ix->b_dev_queries = queries + base;
+        } else {
+            ix->d_queries.ensure(blob_bytes + 16);
+            CK(cudaMemcpyAsync(ix->d_queries.p, queries + base, blob_bytes, cudaMemcpyHostToDevice, st));
+            ix->b_dev_queries = ix->d_queries.as<char>();
+        }
+        ix->d_qoff.ensure((nq + 1) * 8);
+        ix->d_koff.ensure((nq + 1) * 4);
+        ix->d_thr.ensure(std::max<size_t>(nq, 1) * 4);
+        CK(cudaMemcpyAsync(ix->d_qoff.p, ix->b_qoff.data(), (nq + 1) * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ix->d_koff.p, ix->b_koff.data(), (nq + 1) * 4, cudaMemcpyHostToDevice, st));
+        if (nq) CK(cudaMemcpyAsync(ix->d_thr.p, ix->b_thr.data(), nq * 4, cudaMemcpyHostToDevice, st));
+    }
+    ix->d_hashes.ensure(std::max<uint64_t>(1, kmers) * ix->num_hashes * 8);
+    if (kmers) {
+        HashParams hp{};
+        hp.queries = ix->b_dev_queries;
+        hp.qoff = ix->d_qoff.as<uint64_t>();
+        hp.koff = ix->d_koff.as<uint32_t>();
+        hp.nq = nq;
+        hp.total_kmers = ix->b_total_kmers;
+        hp.k = k;
+        hp.h = ix->num_hashes;
+        hp.canonicalize = ix->canonicalize;
+        hp.hashes = ix->d_hashes.as<uint64_t>();
+        hp.first_bad = ix->d_flags.as<int>();
+        PhaseScope ps(ix, PH_HASH, st);
+        hash_kmers_kernel<<<div_ceil<uint32_t>(ix->b_total_kmers, 128), 128, 0, st>>>(hp);
+        CK(cudaGetLastError());
+        ix->tm.kernel_launches++;
+    }
+    ix->tm.kmers += kmers;
+    ix->tm.queries += nq;
+}
+
+ScoreParams base_params(cobsgpu_index* ix, const uint32_t* d_qlist, uint32_t n_slots) {
+    ScoreParams sp{};
+    sp.tiles = ix->d_tiles;
+    sp.n_tiles = static_cast<uint32_t>(ix->tiles.size());
+    sp.h = ix->num_hashes;
+    sp.hashes = ix->d_hashes.as<uint64_t>();
+    sp.koff = ix->d_koff.as<uint32_t>();
+    sp.qlist = d_qlist;
+    sp.nq_items = n_slots;
+    sp.thr = ix->d_thr.as<uint32_t>();
+    sp.dense_pitch = ix->dense_pitch;
+    return sp;
+}
+
+uint32_t bits_for(uint32_t v) {
+    uint32_t b = 0;
+    while (v) {
+        ++b;
+        v >>= 1;
+    }
+    return std::max<uint32_t>(b, 1);
+}
+
+// One pass over `n_slots` queries (slot i = batch query qlist[i], or i when d_qlist is null):
+// K2 (+ dense_to_cand for long queries) fills the candidate lists, K3 sorts them.  Leaves
+// d_cand_count / d_res_count per slot and the sorted keys in d_cand (or d_scratch, see
+// *large_in_scratch).  max_T = largest k-mer count among the slots.
+void run_pass(cobsgpu_index* ix, const uint32_t* d_qlist, uint32_t n_slots, uint32_t cap,
+              bool long_mode, uint32_t max_T, uint64_t limit, bool* large_in_scratch,
+              cudaStream_t st) {
+    cap = std::max<uint32_t>(cap, 1);
+    ix->d_cand.ensure(static_cast<uint64_t>(n_slots) * cap * 8);
+    ix->d_cand_count.ensure(n_slots * 4);
+    ix->d_res_count.ensure(n_slots * 4);
+    CK(cudaMemsetAsync(ix->d_cand_count.p, 0, n_slots * 4, st));
+    ScoreParams sp = base_params(ix, d_qlist, n_slots);
+    sp.cand_count = ix->d_cand_count.as<uint32_t>();
+    sp.cand = ix->d_cand.as<uint64_t>();
+    sp.cap = cap;
+    if (!long_mode) {
+        launch_score(ix, sp, MODE_CAND, st);
+    } else {
+        ix->d_dense.ensure(static_cast<uint64_t>(n_slots) * ix->dense_pitch * 4);
+        CK(cudaMemsetAsync(ix->d_dense.p, 0, static_cast<uint64_t>(n_slots) * ix->dense_pitch * 4, st));
+        sp.dense32 = ix->d_dense.as<uint32_t>();
+        launch_score(ix, sp, MODE_DENSE32, st);
+        if (!ix->pages.empty()) {
+            PhaseScope ps(ix, PH_SELECT, st);
+            DenseToCandParams dp{};
+            dp.dense32 = sp.dense32;
+            dp.dense_pitch = ix->dense_pitch;
+            dp.qlist = d_qlist;
+            dp.thr = ix->d_thr.as<uint32_t>();
+            const uint32_t np = static_cast<uint32_t>(ix->pages.size());
+            dp.seg_dense_off = ix->d_seg;
+            dp.seg_n_real = ix->d_seg + np;
+            dp.seg_doc_base = ix->d_seg + 2 * np;
+            dp.n_seg = np;
+            dp.cand_count = sp.cand_count;
+            dp.cand = sp.cand;
+            dp.cap = cap;
+            uint32_t max_real = 1;
+            for (auto& lp : ix->pages) max_real = std::max(max_real, lp.n_real);
+            dim3 grid(std::min<uint32_t>(div_ceil<uint32_t>(max_real, 256), 64), n_slots);
+            dense_to_cand_kernel<<<grid, 256, 0, st>>>(dp);
+            CK(cudaGetLastError());
+            ix->tm.kernel_launches++;
+        }
+    }
+    PhaseScope ps(ix, PH_SELECT, st);
+    result_counts_kernel<<<div_ceil<uint32_t>(n_slots, 256), 256, 0, st>>>(
+        sp.cand_count, n_slots, cap, limit, ix->d_res_count.as<uint32_t>(), ix->d_flags.as<int>() + 1);
+    CK(cudaGetLastError());
+    sort_small_kernel<<<n_slots, SORT_SMALL_THREADS, 0, st>>>(sp.cand, sp.cand_count, cap, 1);
+    CK(cudaGetLastError());
+    ix->tm.kernel_launches += 2;
+    *large_in_scratch = false;
+    if (cap > SORT_SMALL_MAX) {
+        ix->d_scratch.ensure(static_cast<uint64_t>(n_slots) * cap * 8);
+        SortLargeParams lp{};
+        lp.cand = sp.cand;
+        lp.scratch = ix->d_scratch.as<uint64_t>();
+        lp.cand_count = sp.cand_count;
+        lp.cap = cap;
+        // digits over the varying key bits only: document id (low word) then ~score
+        const uint32_t doc_bits = bits_for(ix->shard_doc_end ? ix->shard_doc_end - 1 : 0);
+        const uint32_t score_bits = bits_for(max_T);
+        uint32_t n = 0;
+        for (uint32_t b = 0; b < doc_bits; b += 8) lp.digit_shift[n++] = b;
+        for (uint32_t b = 0; b < score_bits; b += 8) lp.digit_shift[n++] = 32 + b;
+        lp.n_pass = n;
+        *large_in_scratch = (n & 1) != 0;
+        sort_large_kernel<<<n_slots, SORT_LARGE_THREADS, 0, st>>>(lp);
+        CK(cudaGetLastError());
+        ix->tm.kernel_launches++;
+    }
+}
+
+struct HostList {
+    std::vector<uint64_t> off;   // [n_slots + 1]
+    std::vector<uint32_t> doc, score;
+};
+
+// CSR formatting of a finished pass + copy to the host (slot order)
+void fetch_pass(cobsgpu_index* ix, const uint32_t* d_qlist, uint32_t n_slots, uint32_t cap,
+                bool large_in_scratch, HostList* out, std::vector<uint32_t>* cand_counts,
+                cudaStream_t st) {
+    {
+        PhaseScope ps(ix, PH_SELECT, st);
+        ix->d_offsets.ensure((n_slots + 1) * 8);
+        scan_offsets_kernel<<<1, 1024, 0, st>>>(ix->d_res_count.as<uint32_t>(), n_slots,
+                                                ix->d_offsets.as<uint64_t>());
+        CK(cudaGetLastError());
+        ix->tm.kernel_launches++;
+    }
+    out->off.resize(n_slots + 1);
+    cand_counts->resize(n_slots);
+    {
+        PhaseScope ps(ix, PH_D2H, st);
+        ix->h_off.ensure((n_slots + 1) * 8);
+        ix->h_counts.ensure(n_slots * 4);
+        CK(cudaMemcpyAsync(ix->h_off.p, ix->d_offsets.p, (n_slots + 1) * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ix->h_counts.p, ix->d_cand_count.p, n_slots * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    std::memcpy(out->off.data(), ix->h_off.p, (n_slots + 1) * 8);
+    std::memcpy(cand_counts->data(), ix->h_counts.p, n_slots * 4);
+    const uint64_t total = out->off[n_slots];
+    out->doc.resize(total);
+    out->score.resize(total);
+    if (total == 0) return;
+    ix->d_out_doc.ensure(total * 4);
+    ix->d_out_score.ensure(total * 4);
+    {
+        PhaseScope ps(ix, PH_SELECT, st);
+        GatherParams gp{};
+        gp.cand = ix->d_cand.as<uint64_t>();
+        gp.scratch = ix->d_scratch.as<uint64_t>();
+        gp.cand_count = ix->d_cand_count.as<uint32_t>();
+        gp.res_count = ix->d_res_count.as<uint32_t>();
+        gp.qlist = nullptr;   // CSR is in slot order
+        gp.cap = cap;
+        gp.large_in_scratch = large_in_scratch ? 1 : 0;
+        gp.offsets = ix->d_offsets.as<uint64_t>();
+        gp.out_doc = ix->d_out_doc.as<uint32_t>();
+        gp.out_score = ix->d_out_score.as<uint32_t>();
+        gather_kernel<<<n_slots, 256, 0, st>>>(gp);
+        CK(cudaGetLastError());
+        ix->tm.kernel_launches++;
+    }
+    {
+        PhaseScope ps(ix, PH_D2H, st);
+        ix->h_doc.ensure(total * 4);
+        ix->h_score.ensure(total * 4);
+        CK(cudaMemcpyAsync(ix->h_doc.p, ix->d_out_doc.p, total * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ix->h_score.p, ix->d_out_score.p, total * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    std::memcpy(out->doc.data(), ix->h_doc.p, total * 4);
+    std::memcpy(out->score.data(), ix->h_score.p, total * 4);
+}
+
+void check_bad_base(cobsgpu_index* ix, uint32_t q0, cudaStream_t st) {
+    int flags[2];
+    CK(cudaMemcpyAsync(flags, ix->d_flags.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (flags[0] != INT_MAX)
+        throw Err{ COBSGPU_ERR_INVALID_BASE,
+                   "Invalid DNA base pair in query string. Only ACGT are allowed. (query " +
+                       std::to_string(q0 + flags[0]) + ")" };
+}
+
+const uint32_t* upload_qlist(cobsgpu_index* ix, const std::vector<uint32_t>& ids, size_t begin,
+                             size_t n, cudaStream_t st) {
+    ix->d_qlist.ensure(std::max<size_t>(n, 1) * 4);
+    CK(cudaMemcpyAsync(ix->d_qlist.p, ids.data() + begin, n * 4, cudaMemcpyHostToDevice, st));
+    return ix->d_qlist.as<uint32_t>();
+}
+
+// exhaustive pass over the given batch queries in workspace-bounded sub-batches; every real
+// document of the shard can become a candidate (cap = shard_real_docs)
+void run_exhaustive(cobsgpu_index* ix, const std::vector<uint32_t>& ids, bool long_mode,
+                    uint64_t limit, std::vector<HostList>* lists,
+                    std::vector<std::pair<uint32_t, uint32_t>>* where, cudaStream_t st) {
+    if (ids.empty()) return;
+    const uint32_t cap = std::max<uint32_t>(ix->shard_real_docs, 1);
+    uint64_t per_q = static_cast<uint64_t>(cap) * 8 * (cap > SORT_SMALL_MAX ? 2 : 1);
+    if (long_mode) per_q += ix->dense_pitch * 4;
+    const size_t sub = static_cast<size_t>(
+        std::max<uint64_t>(1, std::min<uint64_t>(ids.size(), ix->workspace_bytes / std::max<uint64_t>(per_q, 1))));
+    for (size_t b = 0; b < ids.size(); b += sub) {
+        const size_t n = std::min(sub, ids.size() - b);
+        const uint32_t* d_ql = upload_qlist(ix, ids, b, n, st);
+        uint32_t max_T = 1;
+        for (size_t i = 0; i < n; ++i)
+            max_T = std::max(max_T, ix->b_koff[ids[b + i] + 1] - ix->b_koff[ids[b + i]]);
+        bool lis = false;
+        run_pass(ix, d_ql, static_cast<uint32_t>(n), cap, long_mode, max_T, limit, &lis, st);
+        lists->emplace_back();
+        std::vector<uint32_t> counts;
+        fetch_pass(ix, d_ql, static_cast<uint32_t>(n), cap, lis, &lists->back(), &counts, st);
+        for (size_t i = 0; i < n; ++i)
+            (*where)[ids[b + i]] = { static_cast<uint32_t>(lists->size() - 1), static_cast<uint32_t>(i) };
+    }
+}
+
+void search_one_batch(cobsgpu_index* ix, const char* queries, const uint64_t* offsets, uint32_t q0,
+                      uint32_t q1, double threshold, uint64_t limit) {
+    cudaStream_t st = ix->stream;
+    prepare_batch(ix, queries, false, offsets, q0, q1, threshold, st);
+    const uint32_t nq = q1 - q0;
+    std::vector<uint32_t> short_ids, long_ids;
+    for (uint32_t i = 0; i < nq; ++i) {
+        const uint32_t T = ix->b_koff[i + 1] - ix->b_koff[i];
+        (T > 255 ? long_ids : short_ids).push_back(i);
+    }
+    std::vector<HostList> lists;
+    std::vector<std::pair<uint32_t, uint32_t>> where(nq, { 0u, 0u });   // query -> (list, slot)
+    bool identity_single = false;
+
+    if (!short_ids.empty()) {
+        if (threshold <= 0.0) {
+            // every document passes: go straight to the exhaustive path
+            run_exhaustive(ix, short_ids, false, limit, &lists, &where, st);
+        } else {
+            const bool identity = long_ids.empty();
+            const uint32_t* d_ql =
+                identity ? nullptr : upload_qlist(ix, short_ids, 0, short_ids.size(), st);
+            const uint32_t n = static_cast<uint32_t>(short_ids.size());
+            const uint32_t cap = std::min<uint32_t>(ix->max_candidates, std::max<uint32_t>(ix->shard_real_docs, 1));
+            bool lis = false;
+            run_pass(ix, d_ql, n, cap, false, 255, limit, &lis, st);
+            lists.emplace_back();
+            std::vector<uint32_t> counts;
+            fetch_pass(ix, d_ql, n, cap, lis, &lists.back(), &counts, st);
+            std::vector<uint32_t> over;
+            for (uint32_t i = 0; i < n; ++i) {
+                where[short_ids[i]] = { 0u, i };
+                if (counts[i] > cap) over.push_back(short_ids[i]);
+            }
+            // queries with more candidates than slots are redone exhaustively: nothing is
+            // ever dropped silently
+            run_exhaustive(ix, over, false, limit, &lists, &where, st);
+            identity_single = identity && over.empty();
+        }
+    }
+    run_exhaustive(ix, long_ids, true, limit, &lists, &where, st);
+    check_bad_base(ix, q0, st);
+
+    // append to the call's result in query order
+    const uint64_t base = ix->r_off.back();
+    if (identity_single) {
+        const HostList& L = lists[0];
+        for (uint32_t i = 0; i < nq; ++i) ix->r_off.push_back(base + L.off[i + 1]);
+        ix->r_doc.insert(ix->r_doc.end(), L.doc.begin(), L.doc.end());
+        ix->r_score.insert(ix->r_score.end(), L.score.begin(), L.score.end());
+        return;
+    }
+    uint64_t run = base;
+    for (uint32_t i = 0; i < nq; ++i) {
+        if (!lists.empty()) {
+            const HostList& L = lists[where[i].first];
+            const uint32_t s = where[i].second;
+            const uint64_t a = L.off[s], b = L.off[s + 1];
+            ix->r_doc.insert(ix->r_doc.end(), L.doc.begin() + a, L.doc.begin() + b);
+            ix->r_score.insert(ix->r_score.end(), L.score.begin() + a, L.score.begin() + b);
+            run += b - a;
+        }
+        ix->r_off.push_back(run);
+    }
+}
+
+// batch boundaries: at most max_batch queries and a bounded number of k-mers
+uint32_t next_batch_end(const cobsgpu_index* ix, const uint64_t* offsets, uint32_t q0, uint32_t nq) {
+    const uint64_t kmer_budget = 64ull << 20;
+    uint64_t kmers = 0;
+    uint32_t q = q0;
+    while (q < nq && q - q0 < ix->max_batch) {
+        const uint64_t len = offsets[q + 1] - offsets[q];
+        const uint64_t T = len >= ix->term_size ? len - ix->term_size + 1 : 0;
+        if (q > q0 && kmers + T > kmer_budget) break;
+        kmers += T;
+        ++q;
+    }
+    return q;
+}
+
+}  // namespace
+
+// =========================================================================================
+// C ABI
+
+extern "C" {
+
+const char* cobsgpu_last_error(void) { return g_error.c_str(); }
+int cobsgpu_version(void) { return COBSGPU_VERSION; }
+
+int cobsgpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int cobsgpu_index_open(const cobsgpu_index_desc* d, cobsgpu_index** out) {
+    return guarded([&] {
+        if (!d || !out || d->struct_size != sizeof(cobsgpu_index_desc))
+            throw Err{ COBSGPU_ERR_INVALID_ARG, "bad cobsgpu_index_desc" };
+        if (d->n_pages == 0 || !d->signature_sizes)
+            throw Err{ COBSGPU_ERR_INVALID_ARG, "index needs at least one page" };
+        std::unique_ptr<cobsgpu_index> ix(new cobsgpu_index);
+        ix->kind = d->kind;
+        ix->term_size = d->term_size;
+        ix->canonicalize = d->canonicalize;
+        ix->num_hashes = d->num_hashes;
+        ix->n_docs = d->n_docs;
+        ix->n_pages_global = d->n_pages;
+        ix->device = d->device;
+        ix->shard_index = d->shard_index;
+        ix->shard_count = d->shard_count ? d->shard_count : 1;
+        if (d->kind == COBSGPU_KIND_CLASSIC) {
+            if (d->n_pages != 1) throw Err{ COBSGPU_ERR_INVALID_ARG, "classic index has one page" };
+            ix->page_size_src = (static_cast<uint64_t>(d->n_docs) + 7) / 8;
+        } else if (d->kind == COBSGPU_KIND_COMPACT) {
+            ix->page_size_src = d->page_size;
+            if (d->page_size == 0 ||
+                static_cast<uint64_t>(d->n_docs) > 8 * d->page_size * d->n_pages)
+                throw Err{ COBSGPU_ERR_INVALID_ARG, "compact geometry does not cover n_docs" };
+        } else {
+            throw Err{ COBSGPU_ERR_INVALID_ARG, "unknown index kind" };
+        }
+        if (ix->page_size_src * 8 * d->n_pages > 0xFFFFFFFFull)
+            throw Err{ COBSGPU_ERR_INVALID_ARG, "more than 2^32 document columns" };
+        std::vector<uint64_t> sig(d->signature_sizes, d->signature_sizes + d->n_pages);
+        open_common(ix.get(), sig, d->page_data, d->fill_seed);
+        *out = ix.release();
+    });
+}
+
+int cobsgpu_index_open_file(const char* path, int device, uint32_t shard_index,
+                            uint32_t shard_count, cobsgpu_index** out) {
+    return guarded([&] {
+        if (!path || !out) throw Err{ COBSGPU_ERR_INVALID_ARG, "null argument" };
+        std::unique_ptr<IndexFile> f(new IndexFile);
+        std::string err = f->open(path);
+        if (!err.empty()) {
+            const bool io = err.rfind("could not open", 0) == 0 || err.rfind("mmap", 0) == 0;
+            throw Err{ io ? COBSGPU_ERR_IO : COBSGPU_ERR_BAD_FILE, err };
+        }
+        std::unique_ptr<cobsgpu_index> ix(new cobsgpu_index);
+        ix->kind = f->kind;
+        ix->term_size = f->term_size;
+        ix->canonicalize = f->canonicalize;
+        ix->num_hashes = f->num_hashes;
+        ix->n_docs = f->n_docs;
+        ix->n_pages_global = static_cast<uint32_t>(f->signature_sizes.size());
+        ix->page_size_src = f->page_size;
+        ix->device = device;
+        ix->shard_index = shard_index;
+        ix->shard_count = shard_count ? shard_count : 1;
+        ix->doc_names = f->doc_names;
+        if (ix->page_size_src * 8 * ix->n_pages_global > 0xFFFFFFFFull)
+            throw Err{ COBSGPU_ERR_INVALID_ARG, "more than 2^32 document columns" };
+        open_common(ix.get(), f->signature_sizes, f->page_data.data(), 0);
+        f->close();   // the matrix now lives in HBM
+        *out = ix.release();
+    });
+}
+
+void cobsgpu_index_close(cobsgpu_index* idx) { delete idx; }
+
+int cobsgpu_index_get_info(const cobsgpu_index* ix, cobsgpu_index_info* o) {
+    return guarded([&] {
+        if (!ix || !o) throw Err{ COBSGPU_ERR_INVALID_ARG, "null argument" };
+        o->kind = ix->kind;
+        o->term_size = ix->term_size;
+        o->canonicalize = ix->canonicalize;
+        o->num_hashes = ix->num_hashes;
+        o->n_docs = ix->n_docs;
+        o->n_pages = ix->n_pages_global;
+        const bool classic = ix->kind == COBSGPU_KIND_CLASSIC;
+        o->page_size = classic ? 1 : ix->page_size_src;
+        o->row_size = classic ? ix->page_size_src : ix->page_size_src * ix->n_pages_global;
+        o->counts_size = 8 * ix->page_size_src * ix->n_pages_global;
+        o->shard_index = ix->shard_index;
+        o->shard_count = ix->shard_count;
+        o->shard_doc_begin = ix->shard_doc_begin;
+        o->shard_doc_end = ix->shard_doc_end;
+        o->hbm_bytes = ix->hbm_bytes;
+        o->bytes_per_kmer = ix->bytes_per_kmer;
+    });
+}
+
+const char* cobsgpu_index_doc_name(const cobsgpu_index* ix, uint32_t doc) {
+    if (!ix || doc >= ix->doc_names.size()) return nullptr;
+    return ix->doc_names[doc].c_str();
+}
+
+int cobsgpu_set_option(cobsgpu_index* ix, const char* name, int64_t value) {
+    return guarded([&] {
+        if (!ix || !name) throw Err{ COBSGPU_ERR_INVALID_ARG, "null argument" };
+        const std::string n = name;
+        if (n == "max_candidates" && value >= 1) ix->max_candidates = static_cast<uint32_t>(std::min<int64_t>(value, 1 << 24));
+        else if (n == "max_batch" && value >= 1) ix->max_batch = static_cast<uint32_t>(std::min<int64_t>(value, 1 << 22));
+        else if (n == "workspace_mb" && value >= 1) ix->workspace_bytes = static_cast<uint64_t>(value) << 20;
+        else if (n == "timing") ix->timing = value != 0;
+        else throw Err{ COBSGPU_ERR_INVALID_ARG, "unknown option or bad value: " + n };
+    });
+}
+
+int cobsgpu_hash(cobsgpu_index* ix, const char* queries, const uint64_t* offsets, uint32_t nq,
+                 uint64_t* out) {
+    return guarded([&] {
+        if (!ix || !offsets || (!queries && nq)) throw Err{ COBSGPU_ERR_INVALID_ARG, "null argument" };
+        CK(cudaSetDevice(ix->device));
+        uint64_t done = 0;
+        for (uint32_t q0 = 0; q0 < nq;) {
+            const uint32_t q1 = next_batch_end(ix, offsets, q0, nq);
+            prepare_batch(ix, queries, false, offsets, q0, q1, 0.0, ix->stream);
+            const uint64_t n = static_cast<uint64_t>(ix->b_total_kmers) * ix->num_hashes;
+            CK(cudaMemcpyAsync(out + done, ix->d_hashes.p, n * 8, cudaMemcpyDeviceToHost, ix->stream));
+            check_bad_base(ix, q0, ix->stream);
+            done += n;
+            q0 = q1;
+        }
+        resolve_timers(ix);
+    });
+}
+
+int cobsgpu_scores(cobsgpu_index* ix, const char* queries, const uint64_t* offsets, uint32_t nq,
+                   uint32_t* out) {
+    return guarded([&] {
+        if (!ix || !offsets || (!queries && nq) || !out) throw Err{ COBSGPU_ERR_INVALID_ARG, "null argument" };
+        CK(cudaSetDevice(ix->device));
+        cudaStream_t st = ix->stream;
+        const uint64_t counts_size = 8 * ix->page_size_src * ix->n_pages_global;
+        for (uint32_t q0 = 0; q0 < nq;) {
+            const uint32_t q1 = next_batch_end(ix, offsets, q0, nq);
+            prepare_batch(ix, queries, false, offsets, q0, q1, 0.0, st);
+            std::vector<uint32_t> ids[2];   // [0] short (u8 planes suffice), [1] long
+            for (uint32_t i = 0; i < q1 - q0; ++i)
+                ids[ix->b_koff[i + 1] - ix->b_koff[i] > 255 ? 1 : 0].push_back(i);
+            for (int lm = 0; lm < 2; ++lm) {
+                const size_t esz = lm ? 4 : 1;
+                const size_t sub = static_cast<size_t>(std::max<uint64_t>(
+                    1, std::min<uint64_t>(ids[lm].size(), ix->workspace_bytes / (ix->dense_pitch * esz))));
+                for (size_t b = 0; b < ids[lm].size(); b += sub) {
+                    const size_t n = std::min(sub, ids[lm].size() - b);
+                    const uint32_t* d_ql = upload_qlist(ix, ids[lm], b, n, st);
+                    const size_t bytes = n * ix->dense_pitch * esz;
+                    ix->d_dense.ensure(bytes);
+                    CK(cudaMemsetAsync(ix->d_dense.p, 0, bytes, st));
+                    ScoreParams sp = base_params(ix, d_ql, static_cast<uint32_t>(n));
+                    sp.dense8 = ix->d_dense.as<uint8_t>();
+                    sp.dense32 = ix->d_dense.as<uint32_t>();
+                    launch_score(ix, sp, lm ? MODE_DENSE32 : MODE_DENSE8, st);
+                    ix->h_dense.ensure(bytes);
+                    CK(cudaMemcpyAsync(ix->h_dense.p, ix->d_dense.p, bytes, cudaMemcpyDeviceToHost, st));
+                    CK(cudaStreamSynchronize(st));
+                    // shard-local dense layout -> the reference's score_list layout
+                    for (size_t i = 0; i < n; ++i) {
+                        uint32_t* dst = out + static_cast<uint64_t>(q0 + ids[lm][b + i]) * counts_size;
+                        for (auto& lp : ix->pages) {
+                            const uint64_t gcol = static_cast<uint64_t>(lp.global_page) * 8 * ix->page_size_src +
+                                                  8 * lp.byte_begin;
+                            const uint64_t cols = static_cast<uint64_t>(lp.row_bytes) * 8;
+                            if (lm) {
+                                const uint32_t* s = ix->h_dense.as<uint32_t>() + i * ix->dense_pitch + lp.dense_off;
+                                std::memcpy(dst + gcol, s, cols * 4);
+                            } else {
+                                const uint8_t* s = ix->h_dense.as<uint8_t>() + i * ix->dense_pitch + lp.dense_off;
+                                for (uint64_t c = 0; c < cols; ++c) dst[gcol + c] = s[c];
+                            }
+                        }
+                    }
+                }
+            }
+            check_bad_base(ix, q0, st);
+            q0 = q1;
+        }
+        resolve_timers(ix);
+    });
+}
+
+int cobsgpu_search_batch(cobsgpu_index* ix, const char* queries, const uint64_t* offsets,
+                         uint32_t nq, double threshold, uint64_t num_results,
+                         cobsgpu_result* out) {
+    return guarded([&] {
+        if (!ix || !offsets || (!queries && nq) || !out) throw Err{ COBSGPU_ERR_INVALID_ARG, "null argument" };
+        CK(cudaSetDevice(ix->device));
+        ix->r_off.assign(1, 0);
+        ix->r_doc.clear();
+        ix->r_score.clear();
+        for (uint32_t q0 = 0; q0 < nq;) {
+            const uint32_t q1 = next_batch_end(ix, offsets, q0, nq);
+            search_one_batch(ix, queries, offsets, q0, q1, threshold, num_results);
+            q0 = q1;
+        }
+        resolve_timers(ix);
+        out->offsets = ix->r_off.data();
+        out->doc = ix->r_doc.data();
+        out->score = ix->r_score.data();
+    });
+}
+
+int cobsgpu_search_batch_device(cobsgpu_index* ix, const char* d_queries, const uint64_t* offsets,
+                                uint32_t nq, double threshold, uint64_t num_results,
+                                uint32_t results_per_query, uint32_t* d_counts, uint64_t* d_keys,
+                                void* stream) {
+    return guarded([&] {
+        if (!ix || !offsets || (!d_queries && nq) || !d_counts || !d_keys || results_per_query == 0)
+            throw Err{ COBSGPU_ERR_INVALID_ARG, "null argument" };
+        if (nq == 0) return;
+        CK(cudaSetDevice(ix->device));
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        prepare_batch(ix, d_queries, true, offsets, 0, nq, threshold, st);
+        for (uint32_t i = 0; i < nq; ++i)
+            if (ix->b_koff[i + 1] - ix->b_koff[i] > 255)
+                throw Err{ COBSGPU_ERR_INVALID_ARG,
+                           "device-resident path handles queries of at most 255 k-mers" };
+        const uint32_t cap = std::max<uint32_t>(results_per_query, ix->max_candidates);
+        bool lis = false;
+        run_pass(ix, nullptr, nq, cap, false, 255, num_results, &lis, st);
+        PhaseScope ps(ix, PH_SELECT, st);
+        GatherParams gp{};
+        gp.cand = ix->d_cand.as<uint64_t>();
+        gp.scratch = ix->d_scratch.as<uint64_t>();
+        gp.cand_count = ix->d_cand_count.as<uint32_t>();
+        gp.res_count = ix->d_res_count.as<uint32_t>();
+        gp.cap = cap;
+        gp.large_in_scratch = lis ? 1 : 0;
+        gp.out_keys = d_keys;
+        gp.out_counts = d_counts;
+        gp.stride = results_per_query;
+        gather_kernel<<<nq, 256, 0, st>>>(gp);
+        CK(cudaGetLastError());
+        ix->tm.kernel_launches++;
+    });
+}
+
+int cobsgpu_merge_device(int device, uint32_t n_lists, uint32_t nq, uint32_t results_per_query,
+                         const uint32_t* d_counts, const uint64_t* d_keys, uint64_t num_results,
+                         uint32_t out_per_query, uint32_t* d_out_counts, uint64_t* d_out_keys,
+                         void* stream) {
+    return guarded([&] {
+        if (!d_counts || !d_keys || !d_out_counts || !d_out_keys || n_lists == 0 || out_per_query == 0)
+            throw Err{ COBSGPU_ERR_INVALID_ARG, "null argument" };
+        if (nq == 0) return;
+        check_device(device);
+        const uint64_t maxk = static_cast<uint64_t>(n_lists) * results_per_query;
+        if (maxk > MERGE_MAX)
+            throw Err{ COBSGPU_ERR_INVALID_ARG, "merge handles at most 8192 keys per query" };
+        uint32_t np2 = 1;
+        while (np2 < maxk) np2 <<= 1;
+        const size_t smem = static_cast<size_t>(np2) * 8;
+        CK(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(smem)));
+        MergeParams mp{ d_counts, d_keys, n_lists, nq, results_per_query, num_results,
+                        out_per_query, d_out_counts, d_out_keys };
+        merge_kernel<<<nq, 256, smem, static_cast<cudaStream_t>(stream)>>>(mp);
+        CK(cudaGetLastError());
+    });
+}
+
+int cobsgpu_get_timers(const cobsgpu_index* ix, cobsgpu_timers* out) {
+    if (!ix || !out) return COBSGPU_ERR_INVALID_ARG;
+    resolve_timers(const_cast<cobsgpu_index*>(ix));
+    *out = ix->tm;
+    return COBSGPU_OK;
+}
+
+int cobsgpu_reset_timers(cobsgpu_index* ix) {
+    if (!ix) return COBSGPU_ERR_INVALID_ARG;
+    resolve_timers(ix);
+    ix->tm = cobsgpu_timers{};
+    return COBSGPU_OK;
+}
+
+int cobsgpu_debug_read_row(cobsgpu_index* ix, uint32_t page, uint64_t row, uint64_t begin,
+                           uint64_t bytes, uint8_t* out) {
+    return guarded([&] {
+        if (!ix || !out || page >= ix->pages.size()) throw Err{ COBSGPU_ERR_INVALID_ARG, "bad page" };
+        const LocalPage& lp = ix->pages[page];
+        if (row >= lp.sig || begin + bytes > lp.pitch) throw Err{ COBSGPU_ERR_INVALID_ARG, "out of range" };
+        CK(cudaSetDevice(ix->device));
+        CK(cudaMemcpy(out, lp.d_base + row * lp.pitch + begin, bytes, cudaMemcpyDeviceToHost));
+    });
+}
+
+}  // extern "C"

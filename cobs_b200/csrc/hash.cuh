@@ -1,0 +1,163 @@
+// cobs_b200/csrc/hash.cuh -- K1: canonicalise + XXH64 every k-mer of a query batch on-device.
+//
+// Replaces create_hashes (cobs/query/classic_search.cpp:66-107), canonicalize_kmer
+// (cobs/util/query.cpp:143-199) and XXH64 (extlib/xxhash/xxhash.c:665-878, v0.6.5) of the
+// reference.  One thread per (query, k-mer); the h seeds 0..h-1 are evaluated by the same
+// thread.  Output: raw 64-bit hashes, k-mer-major ([kmer][j]); the modulo by the signature
+// size is deferred to the score kernel because compact indices use one modulus per page.
+#pragma once
+
+#include "common.cuh"
+
+namespace cobsgpu {
+
+struct HashParams {
+    const char* queries;      // device: concatenated ASCII queries
+    const uint64_t* qoff;     // device [nq+1]: byte offset of each query in `queries`
+    const uint32_t* koff;     // device [nq+1]: prefix sum of k-mers per query
+    uint32_t nq;
+    uint32_t total_kmers;
+    uint32_t k;               // term_size
+    uint32_t h;               // num_hashes
+    uint32_t canonicalize;
+    uint64_t* hashes;         // device [total_kmers * h]
+    int* first_bad;           // device: min query index holding a non-ACGT base (canonical only)
+};
+
+namespace xxh {
+static constexpr uint64_t P1 = 11400714785074694791ULL;
+static constexpr uint64_t P2 = 14029467366897019727ULL;
+static constexpr uint64_t P3 = 1609587929392839161ULL;
+static constexpr uint64_t P4 = 9650029242287828579ULL;
+static constexpr uint64_t P5 = 2870177450012600261ULL;
+
+__host__ __device__ __forceinline__ uint64_t rotl(uint64_t x, int r) {
+    return (x << r) | (x >> (64 - r));
+}
+__host__ __device__ __forceinline__ uint64_t round(uint64_t acc, uint64_t input) {
+    acc += input * P2;
+    acc = rotl(acc, 31);
+    return acc * P1;
+}
+__host__ __device__ __forceinline__ uint64_t merge(uint64_t acc, uint64_t val) {
+    acc ^= round(0, val);
+    return acc * P1 + P4;
+}
+
+// XXH64 of `len` bytes produced by get(i), i = 0..len-1 (little-endian lane assembly).
+template <typename Get>
+__host__ __device__ __forceinline__ uint64_t hash64(Get get, uint32_t len, uint64_t seed) {
+    auto rd64 = [&](uint32_t p) {
+        uint64_t v = 0;
+#pragma unroll
+        for (int b = 7; b >= 0; --b) v = (v << 8) | static_cast<uint64_t>(get(p + b));
+        return v;
+    };
+    uint32_t p = 0;
+    uint64_t hsh;
+    if (len >= 32) {
+        uint64_t v1 = seed + P1 + P2, v2 = seed + P2, v3 = seed, v4 = seed - P1;
+        do {
+            v1 = round(v1, rd64(p));
+            v2 = round(v2, rd64(p + 8));
+            v3 = round(v3, rd64(p + 16));
+            v4 = round(v4, rd64(p + 24));
+            p += 32;
+        } while (p + 32 <= len);
+        hsh = rotl(v1, 1) + rotl(v2, 7) + rotl(v3, 12) + rotl(v4, 18);
+        hsh = merge(hsh, v1);
+        hsh = merge(hsh, v2);
+        hsh = merge(hsh, v3);
+        hsh = merge(hsh, v4);
+    } else {
+        hsh = seed + P5;
+    }
+    hsh += len;
+    while (p + 8 <= len) {
+        hsh ^= round(0, rd64(p));
+        hsh = rotl(hsh, 27) * P1 + P4;
+        p += 8;
+    }
+    if (p + 4 <= len) {
+        uint64_t v = 0;
+#pragma unroll
+        for (int b = 3; b >= 0; --b) v = (v << 8) | static_cast<uint64_t>(get(p + b));
+        hsh ^= v * P1;
+        hsh = rotl(hsh, 23) * P2 + P3;
+        p += 4;
+    }
+    while (p < len) {
+        hsh ^= static_cast<uint64_t>(get(p)) * P5;
+        hsh = rotl(hsh, 11) * P1;
+        ++p;
+    }
+    hsh ^= hsh >> 33;
+    hsh *= P2;
+    hsh ^= hsh >> 29;
+    hsh *= P3;
+    hsh ^= hsh >> 32;
+    return hsh;
+}
+}  // namespace xxh
+
+// A C G T -> themselves, everything else -> 0
+__host__ __device__ __forceinline__ uint8_t base_fwd(uint8_t c) {
+    return (c == 'A' || c == 'C' || c == 'G' || c == 'T') ? c : 0;
+}
+// complement, everything else -> 0
+__host__ __device__ __forceinline__ uint8_t base_rev(uint8_t c) {
+    return c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : 0;
+}
+
+// Hashes of one k-mer at `s`.  Returns false when canonicalising and a non-ACGT base occurs.
+template <typename Emit>
+__host__ __device__ __forceinline__ bool hash_kmer(const uint8_t* s, uint32_t k, uint32_t h,
+                                                   uint32_t canonicalize, Emit emit) {
+    if (!canonicalize) {
+        for (uint32_t j = 0; j < h; ++j)
+            emit(j, xxh::hash64([&](uint32_t i) { return s[i]; }, k, j));
+        return true;
+    }
+    // the lexicographically smaller of (k-mer, reverse complement): first differing
+    // position from the outside in decides; a tie over the whole first half keeps the
+    // forward strand (cobs/util/query.cpp:155-198)
+    bool reverse = false, good = true;
+    for (uint32_t i = 0; i < k / 2; ++i) {
+        uint8_t f = base_fwd(s[i]), r = base_rev(s[k - 1 - i]);
+        if (f != r) {
+            reverse = f > r;
+            break;
+        }
+    }
+    for (uint32_t i = 0; i < k; ++i) good = good && base_fwd(s[i]) != 0;
+    if (!good) return false;
+    if (reverse) {
+        for (uint32_t j = 0; j < h; ++j)
+            emit(j, xxh::hash64([&](uint32_t i) { return base_rev(s[k - 1 - i]); }, k, j));
+    } else {
+        for (uint32_t j = 0; j < h; ++j)
+            emit(j, xxh::hash64([&](uint32_t i) { return s[i]; }, k, j));
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(128) hash_kmers_kernel(HashParams p) {
+    uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= p.total_kmers) return;
+    // query owning k-mer gid: largest q with koff[q] <= gid
+    uint32_t lo = 0, hi = p.nq;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (p.koff[mid] <= gid) lo = mid;
+        else hi = mid;
+    }
+    uint32_t q = lo;
+    uint32_t t = gid - p.koff[q];
+    const uint8_t* s = reinterpret_cast<const uint8_t*>(p.queries) + p.qoff[q] + t;
+    uint64_t* out = p.hashes + static_cast<uint64_t>(gid) * p.h;
+    bool good = hash_kmer(s, p.k, p.h, p.canonicalize,
+                          [&](uint32_t j, uint64_t v) { out[j] = v; });
+    if (!good) atomicMin(p.first_bad, static_cast<int>(q));
+}
+
+}  // namespace cobsgpu

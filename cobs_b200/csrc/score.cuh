@@ -1,0 +1,380 @@
+// cobs_b200/csrc/score.cuh -- K2: fused row gather + AND + per-document counting (+ threshold).
+//
+// Replaces, in ONE kernel, the reference's per-batch pipeline
+//   read_from_disk   (cobs/query/classic_index/mmap_search_file.cpp:27-40,
+//                     cobs/query/compact_index/mmap_search_file.cpp:34-67)
+//   aggregate_rows   (cobs/query/classic_search.cpp:279-307)
+//   compute_counts_* (cobs/query/classic_search.cpp:213-275, 643-1022)
+// and, in CAND mode, the threshold filter of counts_to_result (classic_search.cpp:121-126).
+//
+// Design (B200, HBM-bound integer work, no tensor cores):
+//   * work item = (query, column tile); a tile is <= W = 512*NCW contiguous bytes of a
+//     signature row (4096*NCW documents).  Persistent CTAs stride over the items.
+//   * one PRODUCER warp per CTA turns raw hashes into row addresses (hash % signature_size,
+//     one modulus per page) and streams the h row slices of every k-mer into a shared-memory
+//     ring with 1-D TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP);
+//     the `rows` scratch buffer of the reference is never materialised.
+//   * NCW CONSUMER warps: each thread owns 16 bytes = 128 documents of the tile, reads the h
+//     slices with 128-bit shared loads, ANDs them, and adds the 128 result bits into
+//     BIT-SLICED (vertical) counters: 8 bit-planes per 32-document word, fed through a
+//     carry-save adder tree over groups of 8 k-mers (~3 LOP3 per word per k-mer) -- a
+//     per-bit extract+add could not keep up with HBM.
+//   * epilogue per item: CAND  -> bit-sliced compare against ceil(threshold*T), survivors are
+//                                 appended (warp-aggregated atomics) as sort keys;
+//                         DENSE8 -> the 128 counts are transposed out of the planes and stored;
+//                         DENSE32-> counts are added into a u32 score vector every 248 k-mers
+//                                   (queries with more than 255 k-mers).
+#pragma once
+
+#include "common.cuh"
+
+namespace cobsgpu {
+
+enum ScoreMode : int { MODE_CAND = 0, MODE_DENSE8 = 1, MODE_DENSE32 = 2 };
+
+// one column tile of one page of the shard held by this device
+struct TileDesc {
+    const uint8_t* base;  // device address of (row 0, first byte of the tile)
+    uint64_t sig;         // rows of the page = modulus for this tile
+    uint32_t pitch;       // bytes between consecutive rows of the page
+    uint32_t bytes;       // bytes of this tile, multiple of 16, <= W
+    uint32_t doc_base;    // global document id of bit 0 of the tile
+    uint32_t n_real;      // real documents in the tile counted from doc_base
+    uint32_t dense_off;   // first column of the tile in the shard-local dense score layout
+    uint32_t pad;
+};
+
+struct ScoreParams {
+    const TileDesc* tiles;
+    uint32_t n_tiles;
+    uint32_t h;
+    const uint64_t* hashes;   // [total_kmers * h] from K1
+    const uint32_t* koff;     // [nq+1] k-mer prefix per query of the batch
+    const uint32_t* qlist;    // optional [nq_items]: batch query index per slot; NULL = identity
+    uint32_t nq_items;
+    uint32_t n_stages;        // ring depth (k-mers in flight per CTA)
+    // MODE_CAND
+    const uint32_t* thr;      // [nq] ceil(threshold * T_q), indexed by batch query
+    uint32_t* cand_count;     // [nq_items]
+    uint64_t* cand;           // [nq_items * cap]
+    uint32_t cap;
+    // MODE_DENSE8 / MODE_DENSE32
+    uint8_t* dense8;          // [nq_items * dense_pitch]
+    uint32_t* dense32;        // [nq_items * dense_pitch] (zero-initialised)
+    uint64_t dense_pitch;     // columns per slot, multiple of 128
+};
+
+static constexpr int SCORE_MAX_THREADS = 160;   // 4 consumer warps + 1 producer warp
+static constexpr int SCORE_PLANES = 8;          // counts up to 255 between flushes
+static constexpr uint32_t SCORE_FLUSH = 248;    // k-mers per DENSE32 flush (multiple of 8)
+
+// full adder over 32 lanes of documents
+#define COBS_CSA(sum, carry, a, b, c)            \
+    {                                            \
+        uint32_t u_ = (a) ^ (b);                 \
+        uint32_t c_ = ((a) & (b)) | (u_ & (c));  \
+        (sum) = u_ ^ (c);                        \
+        (carry) = c_;                            \
+    }
+
+// documents of a 32-bit word whose bit-sliced count is >= thr
+__device__ __forceinline__ uint32_t planes_ge(const uint32_t (&pl)[SCORE_PLANES], uint32_t thr) {
+    if (thr == 0) return 0xFFFFFFFFu;
+    if (thr > 255) return 0u;
+    uint32_t gt = 0, eq = 0xFFFFFFFFu;
+#pragma unroll
+    for (int i = SCORE_PLANES - 1; i >= 0; --i) {
+        if ((thr >> i) & 1u) {
+            eq &= pl[i];
+        } else {
+            gt |= eq & pl[i];
+            eq &= ~pl[i];
+        }
+    }
+    return gt | eq;
+}
+
+__device__ __forceinline__ uint32_t planes_count(const uint32_t (&pl)[SCORE_PLANES], uint32_t bit) {
+    uint32_t c = 0;
+#pragma unroll
+    for (int i = 0; i < SCORE_PLANES; ++i) c |= ((pl[i] >> bit) & 1u) << i;
+    return c;
+}
+
+// counts of documents 4g..4g+3 of a word, one per byte (8x4 bit-matrix transpose by multiply)
+__device__ __forceinline__ uint32_t planes_pack4(const uint32_t (&pl)[SCORE_PLANES], uint32_t g) {
+    uint32_t out = 0;
+#pragma unroll
+    for (int i = 0; i < SCORE_PLANES; ++i) {
+        uint32_t nib = (pl[i] >> (4 * g)) & 0xFu;
+        out |= ((nib * 0x00204081u) & 0x01010101u) << i;
+    }
+    return out;
+}
+
+template <int H, int MODE>
+__global__ void __launch_bounds__(SCORE_MAX_THREADS, 3) score_kernel(const ScoreParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t h = H > 0 ? static_cast<uint32_t>(H) : p.h;
+    const uint32_t ncw = (blockDim.x >> 5) - 1;   // consumer warps; the last warp produces
+    const uint32_t W = ncw * 512;                 // tile width in bytes
+    const uint32_t NS = p.n_stages;
+    const uint32_t stage_bytes = h * W;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = full + NS;
+    uint8_t* data = smem + round_up<uint32_t>(NS * 16, 128);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < NS; ++s) {
+            mbar_init(&full[s], h);      // one arrive.expect_tx per row slice
+            mbar_init(&empty[s], ncw);   // one arrive per consumer warp
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const uint64_t n_items = static_cast<uint64_t>(p.nq_items) * p.n_tiles;
+    uint32_t s = 0, par = 0;   // ring position / phase parity, advanced identically by both roles
+
+    if (warp == ncw) {
+        // ------------------------------ producer warp ------------------------------
+        uint32_t kpr = 32 / h;             // k-mers issued per round, one lane per row slice
+        if (kpr > NS) kpr = NS;
+        const uint32_t my_k = lane / h, my_j = lane - my_k * h;
+        const bool lane_used = my_k < kpr;
+        const uint64_t policy = l2_policy_evict_first();
+        for (uint64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const uint32_t qi = static_cast<uint32_t>(item / p.n_tiles);
+            const uint32_t tile = static_cast<uint32_t>(item - static_cast<uint64_t>(qi) * p.n_tiles);
+            const uint32_t q = p.qlist ? p.qlist[qi] : qi;
+            const TileDesc td = p.tiles[tile];
+            const uint32_t k0 = p.koff[q], T = p.koff[q + 1] - k0;
+            const uint64_t* hq = p.hashes + static_cast<uint64_t>(k0) * h;
+            for (uint32_t t0 = 0; t0 < T; t0 += kpr) {
+                const uint32_t t = t0 + my_k;
+                uint32_t ms = s + my_k, mpar = par;
+                if (ms >= NS) {
+                    ms -= NS;
+                    mpar ^= 1;
+                }
+                if (lane_used && t < T) {
+                    const uint64_t hv = hq[static_cast<uint64_t>(t) * h + my_j];
+                    const uint64_t row = hv % td.sig;   // classic: signature_size; compact: per page
+                    const uint8_t* src = td.base + row * td.pitch;
+                    mbar_wait(&empty[ms], mpar ^ 1);
+                    mbar_arrive_expect_tx(&full[ms], td.bytes);
+                    bulk_g2s(data + ms * stage_bytes + my_j * W, src, td.bytes, &full[ms], policy);
+                }
+                const uint32_t adv = (T - t0 < kpr) ? (T - t0) : kpr;
+                s += adv;
+                if (s >= NS) {
+                    s -= NS;
+                    par ^= 1;
+                }
+                __syncwarp();
+            }
+        }
+        return;
+    }
+
+    // -------------------------------- consumer warps --------------------------------
+    const uint8_t* my = data + threadIdx.x * 16;
+    for (uint64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const uint32_t qi = static_cast<uint32_t>(item / p.n_tiles);
+        const uint32_t tile = static_cast<uint32_t>(item - static_cast<uint64_t>(qi) * p.n_tiles);
+        const uint32_t q = p.qlist ? p.qlist[qi] : qi;
+        const TileDesc td = p.tiles[tile];
+        const uint32_t T = p.koff[q + 1] - p.koff[q];
+        const bool active = threadIdx.x * 16 < td.bytes;
+
+        uint32_t pl[4][SCORE_PLANES];
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+#pragma unroll
+            for (int i = 0; i < SCORE_PLANES; ++i) pl[w][i] = 0;
+
+        // AND of the h row slices of the next k-mer, 128 documents per thread
+        auto fetch = [&](uint32_t (&x)[4]) {
+            mbar_wait(&full[s], par);
+            const uint8_t* src = my + s * stage_bytes;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (active) {
+                v = lds128(src);
+#pragma unroll 4
+                for (uint32_t j = 1; j < h; ++j) {
+                    uint4 u = lds128(src + j * W);
+                    v.x &= u.x;
+                    v.y &= u.y;
+                    v.z &= u.z;
+                    v.w &= u.w;
+                }
+            }
+            x[0] = v.x;
+            x[1] = v.y;
+            x[2] = v.z;
+            x[3] = v.w;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);   // slot may be refilled
+            if (++s == NS) {
+                s = 0;
+                par ^= 1;
+            }
+        };
+
+        // transposes the planes into per-document counts: store (DENSE8) or add (DENSE32)
+        auto flush_dense = [&]() {
+            if (!active) return;
+            const uint64_t col = static_cast<uint64_t>(qi) * p.dense_pitch + td.dense_off +
+                                 threadIdx.x * 128;
+            if (MODE == MODE_DENSE8) {
+                uint4* dst = reinterpret_cast<uint4*>(p.dense8 + col);
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    uint4 lo, hi;
+                    lo.x = planes_pack4(pl[w], 0);
+                    lo.y = planes_pack4(pl[w], 1);
+                    lo.z = planes_pack4(pl[w], 2);
+                    lo.w = planes_pack4(pl[w], 3);
+                    hi.x = planes_pack4(pl[w], 4);
+                    hi.y = planes_pack4(pl[w], 5);
+                    hi.z = planes_pack4(pl[w], 6);
+                    hi.w = planes_pack4(pl[w], 7);
+                    dst[2 * w] = lo;
+                    dst[2 * w + 1] = hi;
+                }
+            } else {
+                uint4* dst = reinterpret_cast<uint4*>(p.dense32 + col);
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        const uint32_t pk = planes_pack4(pl[w], g);
+                        uint4 a = dst[8 * w + g];
+                        a.x += pk & 0xFFu;
+                        a.y += (pk >> 8) & 0xFFu;
+                        a.z += (pk >> 16) & 0xFFu;
+                        a.w += pk >> 24;
+                        dst[8 * w + g] = a;
+                    }
+                }
+            }
+        };
+        auto clear_planes = [&]() {
+#pragma unroll
+            for (int w = 0; w < 4; ++w)
+#pragma unroll
+                for (int i = 0; i < SCORE_PLANES; ++i) pl[w][i] = 0;
+        };
+
+        uint32_t t = 0, acc = 0;   // acc = k-mers held in the planes since the last flush
+        // groups of 8 k-mers through a carry-save adder tree: planes 0..2 are the tree's
+        // ones/twos/fours, the carry of weight 8 ripples into planes 3..7
+        for (; t + 8 <= T; t += 8) {
+            if (MODE == MODE_DENSE32 && acc + 8 > 255) {
+                flush_dense();
+                clear_planes();
+                acc = 0;
+            }
+            uint32_t xa[4], xb[4], t2a[4], t2b[4], t4a[4], t4b[4];
+            fetch(xa);
+            fetch(xb);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) COBS_CSA(pl[w][0], t2a[w], pl[w][0], xa[w], xb[w]);
+            fetch(xa);
+            fetch(xb);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                COBS_CSA(pl[w][0], t2b[w], pl[w][0], xa[w], xb[w]);
+                COBS_CSA(pl[w][1], t4a[w], pl[w][1], t2a[w], t2b[w]);
+            }
+            fetch(xa);
+            fetch(xb);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) COBS_CSA(pl[w][0], t2a[w], pl[w][0], xa[w], xb[w]);
+            fetch(xa);
+            fetch(xb);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                uint32_t t8;
+                COBS_CSA(pl[w][0], t2b[w], pl[w][0], xa[w], xb[w]);
+                COBS_CSA(pl[w][1], t4b[w], pl[w][1], t2a[w], t2b[w]);
+                COBS_CSA(pl[w][2], t8, pl[w][2], t4a[w], t4b[w]);
+#pragma unroll
+                for (int i = 3; i < SCORE_PLANES; ++i) {
+                    const uint32_t n = pl[w][i] & t8;
+                    pl[w][i] ^= t8;
+                    t8 = n;
+                }
+            }
+            acc += 8;
+        }
+        // tail (< 8 k-mers): plain ripple-carry increment
+        for (; t < T; ++t) {
+            if (MODE == MODE_DENSE32 && acc + 1 > 255) {
+                flush_dense();
+                clear_planes();
+                acc = 0;
+            }
+            uint32_t x[4];
+            fetch(x);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                uint32_t c = x[w];
+#pragma unroll
+                for (int i = 0; i < SCORE_PLANES; ++i) {
+                    const uint32_t n = pl[w][i] & c;
+                    pl[w][i] ^= c;
+                    c = n;
+                }
+            }
+            acc += 1;
+        }
+
+        if (MODE == MODE_DENSE8 || MODE == MODE_DENSE32) {
+            flush_dense();
+        } else {
+            // threshold in bit-sliced form, then append the survivors as sort keys
+            const uint32_t thr = p.thr[q];
+            uint32_t m[4], cnt = 0;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const uint32_t d0 = threadIdx.x * 128 + w * 32;   // first document of the word
+                const uint32_t n = td.n_real > d0 ? td.n_real - d0 : 0;   // real ones (no padding)
+                const uint32_t valid = n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u);
+                m[w] = active ? (planes_ge(pl[w], thr) & valid) : 0u;
+                cnt += __popc(m[w]);
+            }
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            if (total != 0) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&p.cand_count[qi], total);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                uint32_t pos = base + incl - cnt;
+                uint64_t* out = p.cand + static_cast<uint64_t>(qi) * p.cap;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    uint32_t mm = m[w];
+                    while (mm) {
+                        const uint32_t b = __ffs(mm) - 1;
+                        mm &= mm - 1;
+                        if (pos < p.cap)
+                            out[pos] = make_key(planes_count(pl[w], b),
+                                                td.doc_base + threadIdx.x * 128 + w * 32 + b);
+                        ++pos;
+                    }
+                }
+            }
+        }
+    }
+}
+
+#undef COBS_CSA
+
+}  // namespace cobsgpu

@@ -1,0 +1,353 @@
+// cobs_b200/csrc/select.cuh -- K3: ordering / top-k of the per-query candidate lists.
+//
+// Replaces the sort + truncation of counts_to_result (cobs/query/classic_search.cpp:128-157,
+// 178-201): candidates were already filtered by the threshold (score kernel epilogue or
+// dense_to_cand_kernel); here each query's keys are sorted ascending, which by construction
+// of make_key() is (score descending, document ascending) -- the reference's comparator
+// (classic_search.cpp:139-143) is a strict total order, so any correct sort reproduces it.
+#pragma once
+
+#include "common.cuh"
+
+namespace cobsgpu {
+
+static constexpr uint32_t SORT_SMALL_MAX = 2048;   // keys sorted in shared memory by one CTA
+static constexpr uint32_t SORT_SMALL_THREADS = 256;
+static constexpr uint32_t SORT_LARGE_THREADS = 1024;
+static constexpr uint32_t MERGE_MAX = 8192;        // keys per query in the shard merge
+
+// in-place ascending bitonic sort of n_pow2 keys in shared memory by the whole CTA
+__device__ __forceinline__ void block_bitonic_sort(uint64_t* s, uint32_t n_pow2) {
+    for (uint32_t k = 2; k <= n_pow2; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+                const uint32_t ixj = i ^ j;
+                if (ixj > i) {
+                    const uint64_t a = s[i], b = s[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) {
+                        s[i] = b;
+                        s[ixj] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t next_pow2(uint32_t n) {
+    uint32_t p = 1;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+// dense u32 scores -> candidate keys (queries with more than 255 k-mers).
+struct DenseToCandParams {
+    const uint32_t* dense32;   // [nq_items * dense_pitch]
+    uint64_t dense_pitch;
+    const uint32_t* qlist;     // optional
+    const uint32_t* thr;       // [nq] by batch query index
+    // page segments of the shard-local dense layout
+    const uint32_t* seg_dense_off;
+    const uint32_t* seg_n_real;
+    const uint32_t* seg_doc_base;
+    uint32_t n_seg;
+    uint32_t* cand_count;
+    uint64_t* cand;
+    uint32_t cap;
+};
+
+__global__ void __launch_bounds__(256) dense_to_cand_kernel(DenseToCandParams p) {
+    const uint32_t qi = blockIdx.y;
+    const uint32_t q = p.qlist ? p.qlist[qi] : qi;
+    const uint32_t thr = p.thr[q];
+    const uint32_t* sc = p.dense32 + static_cast<uint64_t>(qi) * p.dense_pitch;
+    uint64_t* out = p.cand + static_cast<uint64_t>(qi) * p.cap;
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t sgi = 0; sgi < p.n_seg; ++sgi) {
+        const uint32_t n = p.seg_n_real[sgi], off = p.seg_dense_off[sgi], db = p.seg_doc_base[sgi];
+        const uint32_t n_round = round_up<uint32_t>(n, 32);
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round;
+             i += gridDim.x * blockDim.x) {
+            uint32_t v = 0;
+            bool keep = false;
+            if (i < n) {
+                v = sc[off + i];
+                keep = v >= thr;
+            }
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
+            if (bal) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&p.cand_count[qi], __popc(bal));
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (keep) {
+                    const uint32_t pos = base + __popc(bal & ((1u << lane) - 1u));
+                    if (pos < p.cap) out[pos] = make_key(v, db + i);
+                }
+            }
+        }
+    }
+}
+
+// n_q = min(cand_count, cap); sets *overflow when a query produced more than cap candidates
+// and results are unbounded (nothing may be dropped silently); result count = min(n_q, limit).
+__global__ void result_counts_kernel(const uint32_t* cand_count, uint32_t nq, uint32_t cap,
+                                     uint64_t limit, uint32_t* res_count, int* overflow) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    uint32_t c = cand_count[i];
+    if (c > cap) {
+        atomicMin(overflow, static_cast<int>(i));
+        c = cap;
+    }
+    res_count[i] = (limit != 0 && c > limit) ? static_cast<uint32_t>(limit) : c;
+}
+
+// exclusive prefix sum of res_count into 64-bit offsets[nq+1]; single CTA
+__global__ void __launch_bounds__(1024) scan_offsets_kernel(const uint32_t* res_count, uint32_t nq,
+                                                            uint64_t* offsets) {
+    __shared__ uint64_t warp_sum[32];
+    __shared__ uint64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < nq; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const uint64_t v = i < nq ? res_count[i] : 0;
+        uint64_t incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) warp_sum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint64_t w = warp_sum[lane];
+            uint64_t wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint64_t o = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+                if (lane >= d) wi += o;
+            }
+            warp_sum[lane] = wi - w;   // exclusive
+        }
+        __syncthreads();
+        const uint64_t c = carry;
+        const uint64_t excl = c + warp_sum[warp] + incl - v;
+        if (i < nq) offsets[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offsets[nq] = carry;
+}
+
+// one CTA per query: sort the (<= SORT_SMALL_MAX) candidates in shared memory, in place.
+__global__ void __launch_bounds__(SORT_SMALL_THREADS)
+sort_small_kernel(uint64_t* cand, const uint32_t* cand_count, uint32_t cap, uint32_t total_hashes_gt1) {
+    __shared__ uint64_t s[SORT_SMALL_MAX];
+    const uint32_t qi = blockIdx.x;
+    uint32_t n = cand_count[qi];
+    if (n > cap) n = cap;
+    if (n < 2 || n > SORT_SMALL_MAX) return;
+    (void)total_hashes_gt1;
+    uint64_t* keys = cand + static_cast<uint64_t>(qi) * cap;
+    const uint32_t np2 = next_pow2(n);
+    for (uint32_t i = threadIdx.x; i < np2; i += blockDim.x) s[i] = i < n ? keys[i] : KEY_PAD;
+    __syncthreads();
+    block_bitonic_sort(s, np2);
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) keys[i] = s[i];
+}
+
+// one CTA per query with more than SORT_SMALL_MAX candidates: LSD radix sort (8-bit digits)
+// over the varying key bits, ping-ponging between `cand` and `scratch` (same layout).
+// digit_shift[pass] lists the bit offsets to sort on, lowest significance first.
+struct SortLargeParams {
+    uint64_t* cand;
+    uint64_t* scratch;
+    const uint32_t* cand_count;
+    uint32_t cap;
+    uint32_t n_pass;
+    uint32_t digit_shift[8];
+};
+
+__global__ void __launch_bounds__(SORT_LARGE_THREADS) sort_large_kernel(SortLargeParams p) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t warp_cnt[32][256];
+    const uint32_t qi = blockIdx.x;
+    uint32_t n = p.cand_count[qi];
+    if (n > p.cap) n = p.cap;
+    if (n <= SORT_SMALL_MAX) return;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t* src = p.cand + static_cast<uint64_t>(qi) * p.cap;
+    uint64_t* dst = p.scratch + static_cast<uint64_t>(qi) * p.cap;
+    for (uint32_t pass = 0; pass < p.n_pass; ++pass) {
+        const uint32_t shift = p.digit_shift[pass];
+        if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+            atomicAdd(&hist[(src[i] >> shift) & 0xFFu], 1u);
+        __syncthreads();
+        // exclusive scan of the 256 bins by warp 0 (8 bins per lane)
+        if (warp == 0) {
+            uint32_t loc[8], sum = 0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                loc[b] = hist[lane * 8 + b];
+                sum += loc[b];
+            }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            uint32_t run = incl - sum;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                hist[lane * 8 + b] = run;
+                run += loc[b];
+            }
+        }
+        __syncthreads();
+        // stable scatter, one chunk of blockDim.x keys at a time, in input order
+        for (uint32_t base = 0; base < n; base += blockDim.x) {
+            for (uint32_t i = threadIdx.x; i < 32 * 256; i += blockDim.x)
+                (&warp_cnt[0][0])[i] = 0;
+            __syncthreads();
+            const uint32_t i = base + threadIdx.x;
+            const bool valid = i < n;
+            uint64_t key = 0;
+            uint32_t dig = 0, rank = 0;
+            if (valid) {
+                key = src[i];
+                dig = static_cast<uint32_t>(key >> shift) & 0xFFu;
+            }
+            const uint32_t act = __ballot_sync(0xFFFFFFFFu, valid);
+            if (valid) {
+                const uint32_t peers = __match_any_sync(act, dig);
+                rank = __popc(peers & ((1u << lane) - 1u));
+                if (rank == 0) warp_cnt[warp][dig] = __popc(peers);
+            }
+            __syncthreads();
+            // per digit: running offsets across the warps of this chunk
+            if (threadIdx.x < 256) {
+                uint32_t run = hist[threadIdx.x];
+                for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) {
+                    const uint32_t c = warp_cnt[w][threadIdx.x];
+                    warp_cnt[w][threadIdx.x] = run;
+                    run += c;
+                }
+                hist[threadIdx.x] = run;
+            }
+            __syncthreads();
+            if (valid) dst[warp_cnt[warp][dig] + rank] = key;
+            __syncthreads();
+        }
+        uint64_t* tmp = src;
+        src = dst;
+        dst = tmp;
+        __syncthreads();
+    }
+}
+
+// final formatting.  Sorted keys of slot qi live in `cand` (or in `scratch` when the large
+// sort ran an odd number of passes).  CSR mode: doc/score arrays at offsets[qi];
+// strided mode: keys at out_keys[q * stride] and counts at out_counts[q].
+struct GatherParams {
+    const uint64_t* cand;
+    const uint64_t* scratch;
+    const uint32_t* cand_count;
+    const uint32_t* res_count;
+    const uint32_t* qlist;     // optional: slot -> batch query
+    uint32_t cap;
+    uint32_t large_in_scratch; // 1 if queries with n > SORT_SMALL_MAX ended in scratch
+    // CSR
+    const uint64_t* offsets;   // by batch query
+    uint32_t* out_doc;
+    uint32_t* out_score;
+    // strided
+    uint64_t* out_keys;
+    uint32_t* out_counts;
+    uint32_t stride;
+};
+
+__global__ void __launch_bounds__(256) gather_kernel(GatherParams p) {
+    const uint32_t qi = blockIdx.x;
+    const uint32_t q = p.qlist ? p.qlist[qi] : qi;
+    uint32_t n = p.cand_count[qi];
+    if (n > p.cap) n = p.cap;
+    const uint32_t r = p.res_count[qi];
+    const uint64_t* keys = ((n > SORT_SMALL_MAX && p.large_in_scratch) ? p.scratch : p.cand) +
+                           static_cast<uint64_t>(qi) * p.cap;
+    if (p.out_keys) {
+        uint64_t* o = p.out_keys + static_cast<uint64_t>(q) * p.stride;
+        for (uint32_t i = threadIdx.x; i < r && i < p.stride; i += blockDim.x) o[i] = keys[i];
+        // more candidates than slots: the list would be incomplete -> flagged, never silent
+        if (threadIdx.x == 0)
+            p.out_counts[q] = p.cand_count[qi] > p.cap ? 0xFFFFFFFFu : (r < p.stride ? r : p.stride);
+    } else {
+        const uint64_t off = p.offsets[q];
+        for (uint32_t i = threadIdx.x; i < r; i += blockDim.x) {
+            const uint64_t k = keys[i];
+            p.out_doc[off + i] = key_doc(k);
+            p.out_score[off + i] = key_score(k);
+        }
+    }
+}
+
+// shard merge: per query concatenate n_lists sorted lists, sort, keep the first `limit`.
+struct MergeParams {
+    const uint32_t* counts;   // [n_lists][nq]
+    const uint64_t* keys;     // [n_lists][nq][stride]
+    uint32_t n_lists, nq, stride;
+    uint64_t limit;
+    uint32_t out_stride;
+    uint32_t* out_counts;     // [nq]
+    uint64_t* out_keys;       // [nq][out_stride]
+};
+
+__global__ void __launch_bounds__(256) merge_kernel(MergeParams p) {
+    extern __shared__ __align__(16) uint64_t ms[];
+    __shared__ uint32_t tot, ovf;
+    const uint32_t q = blockIdx.x;
+    if (threadIdx.x == 0) {
+        uint32_t t = 0, o = 0;
+        for (uint32_t l = 0; l < p.n_lists; ++l) {
+            const uint32_t c = p.counts[static_cast<uint64_t>(l) * p.nq + q];
+            if (c == 0xFFFFFFFFu) o = 1;   // a shard overflowed its candidate slots
+            else t += c < p.stride ? c : p.stride;
+        }
+        tot = t;
+        ovf = o;
+    }
+    __syncthreads();
+    if (ovf) {
+        if (threadIdx.x == 0) p.out_counts[q] = 0xFFFFFFFFu;
+        return;
+    }
+    const uint32_t total = tot;
+    // lists are short; every thread walks the list table
+    uint32_t start = 0;
+    for (uint32_t l = 0; l < p.n_lists; ++l) {
+        uint32_t c = p.counts[static_cast<uint64_t>(l) * p.nq + q];
+        if (c > p.stride) c = p.stride;
+        const uint64_t* src = p.keys + (static_cast<uint64_t>(l) * p.nq + q) * p.stride;
+        for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) ms[start + i] = src[i];
+        start += c;
+    }
+    const uint32_t np2 = next_pow2(total);
+    for (uint32_t i = total + threadIdx.x; i < np2; i += blockDim.x) ms[i] = KEY_PAD;
+    __syncthreads();
+    if (total > 1) block_bitonic_sort(ms, np2);
+    uint32_t r = total;
+    if (p.limit != 0 && r > p.limit) r = static_cast<uint32_t>(p.limit);
+    if (r > p.out_stride) r = p.out_stride;
+    uint64_t* o = p.out_keys + static_cast<uint64_t>(q) * p.out_stride;
+    for (uint32_t i = threadIdx.x; i < r; i += blockDim.x) o[i] = ms[i];
+    if (threadIdx.x == 0) p.out_counts[q] = r;
+}
+
+}  // namespace cobsgpu

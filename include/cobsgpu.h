@@ -1,0 +1,209 @@
+/*
+ * include/cobsgpu.h -- C ABI of libcobsgpu.so, the B200 (sm_100a) implementation of the
+ * COBS query hot path:  per-k-mer XXH64 -> signature-row lookup -> AND of the h selected
+ * bit-rows -> per-document hit counts -> threshold / ordered top-k.
+ *
+ * Plain C: opaque handles, pointers and sizes, `int` status codes plus
+ * cobsgpu_last_error().  No exceptions, STL or torch types cross this boundary.
+ * Each entry point cites the reference interface it replaces (paths relative to the
+ * bingmann/cobs source tree).  The C++ drop-in classes (cobs::ClassicSearch, ...) in
+ * cobs_b200/host/ and the Python/ctypes binding in cobs_b200/ sit on top of exactly these
+ * symbols; INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * There is NO CPU fallback: every compute entry point returns COBSGPU_ERR_CUDA when no
+ * sm_100-class device is usable.
+ */
+#ifndef COBSGPU_H
+#define COBSGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COBSGPU_VERSION 1
+
+/* status codes */
+#define COBSGPU_OK 0
+#define COBSGPU_ERR_INVALID_ARG 1
+#define COBSGPU_ERR_CUDA 2
+#define COBSGPU_ERR_OOM 3
+/* query shorter than term_size: the reference prints "query too short ..." and exits
+ * (cobs/query/classic_search.cpp:431-433) */
+#define COBSGPU_ERR_QUERY_TOO_SHORT 4
+/* non-ACGT base in a canonicalising index: the reference die()s
+ * (cobs/query/classic_search.cpp:93-96) */
+#define COBSGPU_ERR_INVALID_BASE 5
+/* bad magic / version: FileIOException in the reference (cobs/file/header.hpp:23-53) */
+#define COBSGPU_ERR_BAD_FILE 6
+#define COBSGPU_ERR_IO 7
+
+#define COBSGPU_KIND_CLASSIC 0
+#define COBSGPU_KIND_COMPACT 1
+
+typedef struct cobsgpu_index cobsgpu_index;
+
+/*
+ * Description of one index to load into HBM.  Mirrors what an IndexSearchFile exposes
+ * (cobs/query/index_file.hpp:19-35) plus the raw bit matrix the mmap variants read
+ * (cobs/query/classic_index/mmap_search_file.cpp:19-42,
+ *  cobs/query/compact_index/mmap_search_file.cpp:16-67).
+ * A classic index is described as ONE page with page_size = row_size = ceil(n_docs/8).
+ */
+typedef struct cobsgpu_index_desc {
+    uint32_t struct_size;       /* sizeof(cobsgpu_index_desc) */
+    int32_t kind;               /* COBSGPU_KIND_* */
+    uint32_t term_size;         /* k */
+    uint32_t canonicalize;      /* 0 or 1 */
+    uint32_t num_hashes;        /* h */
+    uint32_t n_docs;            /* real documents (file_names().size()) */
+    uint32_t n_pages;           /* classic: 1 */
+    uint32_t reserved0;
+    uint64_t page_size;         /* bytes per row per page in the source layout */
+    const uint64_t* signature_sizes;  /* [n_pages] rows per page */
+    /* [n_pages] host pointers, row-major, row stride page_size; NULL => procedural
+     * bits from fill_seed (synthetic benchmark indices; same function as
+     * oracle_fill_word) */
+    const uint8_t* const* page_data;
+    uint64_t fill_seed;
+    int32_t device;             /* CUDA device ordinal */
+    /* document-axis shard held by this handle: shard_index of shard_count.
+     * Classic: contiguous column ranges cut at multiples of 128 documents; compact:
+     * contiguous page ranges balanced by bytes.  Results carry GLOBAL document ids. */
+    uint32_t shard_index;
+    uint32_t shard_count;
+    uint32_t reserved1;
+} cobsgpu_index_desc;
+
+typedef struct cobsgpu_index_info {
+    int32_t kind;
+    uint32_t term_size;
+    uint32_t canonicalize;
+    uint32_t num_hashes;
+    uint32_t n_docs;        /* real documents of the whole index */
+    uint32_t n_pages;
+    uint64_t page_size;     /* IndexSearchFile::page_size(): classic 1, compact header page_size */
+    uint64_t row_size;      /* IndexSearchFile::row_size() */
+    uint64_t counts_size;   /* IndexSearchFile::counts_size() */
+    uint32_t shard_index;
+    uint32_t shard_count;
+    uint32_t shard_doc_begin;   /* first global column held by this shard */
+    uint32_t shard_doc_end;     /* one past the last column held (padded columns included) */
+    uint64_t hbm_bytes;         /* bytes of signature matrix resident on the device */
+    uint64_t bytes_per_kmer;    /* algorithmic bytes per query k-mer for THIS shard:
+                                   h * (unpadded row bytes held) */
+} cobsgpu_index_info;
+
+/* Result lists of one batch, CSR.  Query q owns entries [offsets[q], offsets[q+1]),
+ * ordered like counts_to_result (cobs/query/classic_search.cpp:109-202): score
+ * descending, then document ascending.  Host memory owned by the index handle, valid
+ * until the next call on that handle. */
+typedef struct cobsgpu_result {
+    const uint64_t* offsets; /* [nq + 1] */
+    const uint32_t* doc;     /* global document ids */
+    const uint32_t* score;
+} cobsgpu_result;
+
+/* Accumulated device-side phase times (CUDA events) and launch counts since the last
+ * reset.  Phase names follow the reference's Timer keys
+ * (cobs/query/classic_search.cpp:329,380,386,392): "hashes" = K1, "io"+"and rows"+
+ * "add rows" = the fused score kernel, "sort results" = select. */
+typedef struct cobsgpu_timers {
+    double hashes_ms;
+    double score_ms;
+    double select_ms;
+    double h2d_ms;
+    double d2h_ms;
+    uint64_t kernel_launches;
+    uint64_t score_launches;
+    uint64_t kmers;          /* query k-mers processed */
+    uint64_t queries;
+} cobsgpu_timers;
+
+const char* cobsgpu_last_error(void);
+int cobsgpu_version(void);
+/* number of usable CUDA devices (0 => every compute call fails with COBSGPU_ERR_CUDA) */
+int cobsgpu_device_count(void);
+
+/* replaces: IndexSearchFile construction + initialize_mmap (cobs/util/query.cpp:38-88) */
+int cobsgpu_index_open(const cobsgpu_index_desc* desc, cobsgpu_index** out);
+/* replaces: ClassicSearch(std::string path) auto-detection (cobs/query/classic_search.cpp:51-64),
+ * header parsing (cobs/file/classic_index_header.cpp:38-50, compact_index_header.cpp:44-65) */
+int cobsgpu_index_open_file(const char* path, int device, uint32_t shard_index,
+                            uint32_t shard_count, cobsgpu_index** out);
+void cobsgpu_index_close(cobsgpu_index* idx);
+int cobsgpu_index_get_info(const cobsgpu_index* idx, cobsgpu_index_info* out);
+/* IndexSearchFile::file_names()[doc].c_str(); NULL for synthetic indices */
+const char* cobsgpu_index_doc_name(const cobsgpu_index* idx, uint32_t doc);
+
+/* options: "max_candidates" (per-query candidate slots of the fused threshold path,
+ * default 1024), "max_batch" (queries per device batch, default 16384),
+ * "workspace_mb" (bound for the exhaustive path, default 1024), "timing" (0/1) */
+int cobsgpu_set_option(cobsgpu_index* idx, const char* name, int64_t value);
+
+/*
+ * Queries are passed as one blob of ASCII characters plus nq+1 offsets
+ * (query q = blob[offsets[q] .. offsets[q+1])).
+ */
+
+/* K1 only.  replaces: create_hashes (cobs/query/classic_search.cpp:66-107).
+ * out receives, query after query, (len_q - k + 1) * h raw 64-bit XXH64 values. */
+int cobsgpu_hash(cobsgpu_index* idx, const char* queries, const uint64_t* offsets,
+                 uint32_t nq, uint64_t* out_hashes);
+
+/* K1 + K2, exhaustive.  replaces: search_index_file (cobs/query/classic_search.cpp:309-401):
+ * out_scores[q * counts_size + d] = hit count of column d (padded columns included, the
+ * reference's score_list layout).  Columns outside this handle's shard are left untouched. */
+int cobsgpu_scores(cobsgpu_index* idx, const char* queries, const uint64_t* offsets,
+                   uint32_t nq, uint32_t* out_scores);
+
+/* K1 + K2 + K3.  replaces: ClassicSearch::search (cobs/query/classic_search.cpp:403-505)
+ * for a batch of queries over one index: documents with score >= ceil(threshold * T_q),
+ * ordered (score desc, doc asc), at most num_results per query (0 = all). */
+int cobsgpu_search_batch(cobsgpu_index* idx, const char* queries,
+                         const uint64_t* offsets, uint32_t nq, double threshold,
+                         uint64_t num_results, cobsgpu_result* out);
+
+/*
+ * Device-resident variant used by the multi-GPU path and by bench.py's "value" leg:
+ * d_queries is a DEVICE pointer (offsets stay on the host, they drive the launch
+ * geometry).  Results stay on the device in caller-provided buffers:
+ *   d_counts[nq]            number of results of query q (<= results_per_query)
+ *   d_keys[nq * results_per_query]   sorted keys; key = (~score << 32) | doc, ascending
+ * A query whose candidates overflowed the per-query candidate slots
+ * (max(results_per_query, "max_candidates")) gets d_counts[q] = UINT32_MAX instead of an
+ * incomplete list (nothing is silently dropped); redo it through cobsgpu_search_batch.
+ * Queries are limited to 255 k-mers on this path.
+ * All work is enqueued on `stream` (a cudaStream_t, may be 0) and is asynchronous.
+ */
+int cobsgpu_search_batch_device(cobsgpu_index* idx, const char* d_queries,
+                                const uint64_t* offsets, uint32_t nq,
+                                double threshold, uint64_t num_results,
+                                uint32_t results_per_query, uint32_t* d_counts,
+                                uint64_t* d_keys, void* stream);
+
+/* K3 merge for document-sharded indices: n_lists per-query lists (e.g. the all-gathered
+ * outputs of cobsgpu_search_batch_device from every rank, laid out
+ * [n_lists][nq][results_per_query]) are merged into one ordered list per query of at most
+ * num_results (0 = results_per_query * n_lists capped at out_per_query) entries.
+ * Device pointers; asynchronous on `stream`. */
+int cobsgpu_merge_device(int device, uint32_t n_lists, uint32_t nq,
+                         uint32_t results_per_query, const uint32_t* d_counts,
+                         const uint64_t* d_keys, uint64_t num_results,
+                         uint32_t out_per_query, uint32_t* d_out_counts,
+                         uint64_t* d_out_keys, void* stream);
+
+int cobsgpu_get_timers(const cobsgpu_index* idx, cobsgpu_timers* out);
+int cobsgpu_reset_timers(cobsgpu_index* idx);
+
+/* Raw access for tests and the loader: copy `bytes` bytes of row `row` of local page
+ * `page` (shard-local column bytes, starting at byte `begin`) back to the host. */
+int cobsgpu_debug_read_row(cobsgpu_index* idx, uint32_t page, uint64_t row,
+                           uint64_t begin, uint64_t bytes, uint8_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COBSGPU_H */
