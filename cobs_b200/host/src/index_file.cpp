@@ -1,0 +1,72 @@
+// IndexSearchFile: loads an index file into HBM through the C ABI and exposes the reference's
+// getters (cobs/query/index_file.hpp:19-35, classic_index/search_file.cpp:15-23,
+// compact_index/search_file.cpp:15-32).
+#include <cobs/file/file_io_exception.hpp>
+#include <cobs/query/index_file.hpp>
+#include <cobs/settings.hpp>
+#include <cobs/util/error_handling.hpp>
+#include <cobs/util/file.hpp>
+
+#include <cobsgpu.h>
+
+#include <cstring>
+
+namespace cobs {
+
+IndexSearchFile::IndexSearchFile(const fs::path& path, int kind) {
+    // the reference throws FileIOException("invalid file type") when the magic word does not
+    // match the class that was asked for (cobs/file/header.hpp:23-29)
+    if (kind == 0 && !file_has_header<ClassicIndexHeader>(path))
+        throw FileIOException("invalid file type");
+    if (kind == 1 && !file_has_header<CompactIndexHeader>(path))
+        throw FileIOException("invalid file type");
+    const unsigned n = gopt_gpus ? gopt_gpus : 1;
+    for (unsigned s = 0; s < n; ++s) {
+        cobsgpu_index* h = nullptr;
+        int rc = cobsgpu_index_open_file(path.string().c_str(), gopt_gpu_device + int(s), s, n, &h);
+        if (rc != COBSGPU_OK) {
+            for (cobsgpu_index* o : shards_) cobsgpu_index_close(o);
+            shards_.clear();
+            std::string msg = cobsgpu_last_error();
+            if (rc == COBSGPU_ERR_BAD_FILE) throw FileIOException(msg);
+            if (rc == COBSGPU_ERR_IO) exit_error(msg);   // like open_file(): print + exit
+            throw std::runtime_error("cobs GPU index: " + msg);
+        }
+        shards_.push_back(h);
+    }
+    cobsgpu_index_info info;
+    cobsgpu_index_get_info(shards_[0], &info);
+    term_size_ = info.term_size;
+    canonicalize_ = static_cast<uint8_t>(info.canonicalize);
+    row_size_ = info.row_size;
+    page_size_ = info.page_size;
+    num_hashes_ = info.num_hashes;
+    counts_size_ = info.counts_size;
+    file_names_.resize(info.n_docs);
+    for (uint32_t d = 0; d < info.n_docs; ++d) file_names_[d] = cobsgpu_index_doc_name(shards_[0], d);
+}
+
+IndexSearchFile::~IndexSearchFile() {
+    for (cobsgpu_index* h : shards_) cobsgpu_index_close(h);
+}
+
+//! Source-compatibility shim: copies `size` bytes starting at byte `begin` of the rows selected
+//! by the raw hashes back from HBM, laid out like the reference's rows buffer.  Classic
+//! indices only (the modulo is per page for compact ones); not on the search path.
+void IndexSearchFile::read_from_disk(
+    const std::vector<size_t>& hashes, uint8_t* rows,
+    size_t begin, size_t size, size_t buffer_size) {
+    if (page_size_ != 1 || shards_.size() != 1)
+        die_with_message("read_from_disk() is only kept for single-GPU classic indices");
+    // signature_size is not part of the public getters: recover it from the handle
+    cobsgpu_index_info info;
+    cobsgpu_index_get_info(shards_[0], &info);
+    if (signature_sizes_.empty()) die_with_message("read_from_disk(): signature size unknown");
+    for (size_t i = 0; i < hashes.size(); ++i) {
+        uint64_t row = hashes[i] % signature_sizes_[0];
+        if (cobsgpu_debug_read_row(shards_[0], 0, row, begin, size, rows + i * buffer_size) != COBSGPU_OK)
+            die_with_message(cobsgpu_last_error());
+    }
+}
+
+} // namespace cobs
