@@ -103,6 +103,7 @@ SYMBOLS = {
                                           C.POINTER(C.c_void_p)]),
     "cobsgpu_index_close": (None, [C.c_void_p]),
     "cobsgpu_index_get_info": (C.c_int, [C.c_void_p, C.POINTER(IndexInfo)]),
+    "cobsgpu_index_signature_size": (C.c_uint64, [C.c_void_p, C.c_uint32]),
     "cobsgpu_index_doc_name": (C.c_char_p, [C.c_void_p, C.c_uint32]),
     "cobsgpu_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "cobsgpu_hash": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),

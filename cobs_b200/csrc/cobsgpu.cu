@@ -134,7 +134,7 @@ struct cobsgpu_index {
     int device = 0;
     uint32_t shard_index = 0, shard_count = 1;
     std::vector<std::string> doc_names;
-    std::unique_ptr<IndexFile> file;
+    std::vector<uint64_t> signature_sizes;   // per GLOBAL page
 
     // HBM layout
     std::vector<LocalPage> pages;
@@ -397,6 +397,7 @@ void open_common(cobsgpu_index* ix, const std::vector<uint64_t>& sig,
     for (uint64_t s : sig)
         if (s == 0) throw Err{ COBSGPU_ERR_INVALID_ARG, "signature_size must be > 0" };
 
+    ix->signature_sizes = sig;
     build_layout(ix, sig);
     CK(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
     ix->own_stream = true;
@@ -972,6 +973,11 @@ int cobsgpu_index_get_info(const cobsgpu_index* ix, cobsgpu_index_info* o) {
         o->hbm_bytes = ix->hbm_bytes;
         o->bytes_per_kmer = ix->bytes_per_kmer;
     });
+}
+
+uint64_t cobsgpu_index_signature_size(const cobsgpu_index* ix, uint32_t page) {
+    if (!ix || page >= ix->signature_sizes.size()) return 0;
+    return ix->signature_sizes[page];
 }
 
 const char* cobsgpu_index_doc_name(const cobsgpu_index* ix, uint32_t doc) {

@@ -60,10 +60,13 @@ class ShardedSearch:
         if self.world == 1:
             k = self.out_per_query(num_results)
             return counts, keys[:, :k]
-        all_counts = torch.empty((self.world, nq), dtype=torch.int32, device=dev)
-        all_keys = torch.empty((self.world, nq, self.rpq), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(all_counts, counts, group=self.group)
-        dist.all_gather_into_tensor(all_keys, keys, group=self.group)
+        # rank-major concatenation along dim 0 (the layout both NCCL and gloo accept)
+        flat_counts = torch.empty(self.world * nq, dtype=torch.int32, device=dev)
+        flat_keys = torch.empty((self.world * nq, self.rpq), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(flat_counts, counts, group=self.group)
+        dist.all_gather_into_tensor(flat_keys, keys, group=self.group)
+        all_counts = flat_counts.view(self.world, nq)
+        all_keys = flat_keys.view(self.world, nq, self.rpq)
         k = self.out_per_query(num_results)
         out_counts = torch.empty(nq, dtype=torch.int32, device=dev)
         out_keys = torch.empty((nq, k), dtype=torch.int64, device=dev)

@@ -1,0 +1,182 @@
+// cobs -- command line front-end of the B200 query path.  `cobs query` is a drop-in for the
+// reference's subtool (src/cobs.cpp:410-527): same flags and defaults, same stdout format
+// ("doc\tscore" per result, "*comment\t<count>" per FASTA record), TIMER line on stderr.
+// FASTA records are searched in GPU batches instead of one at a time.
+#include <cobs/query/classic_index/mmap_search_file.hpp>
+#include <cobs/query/classic_search.hpp>
+#include <cobs/query/compact_index/mmap_search_file.hpp>
+#include <cobs/settings.hpp>
+#include <cobs/util/error_handling.hpp>
+#include <cobs/util/file.hpp>
+
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace {
+
+void usage_query(std::ostream& os) {
+    os << "Usage: cobs query [options] [query]\n\n"
+          "Parameters:\n"
+          "  [query]              the text sequence to search for\n"
+          "Options:\n"
+          "  -i, --index <path>   path to index file(s), may be given several times\n"
+          "  -f, --file <path>    query (fasta) file to process\n"
+          "  -t, --threshold <x>  threshold in percentage of terms in query matching, default: 0.8\n"
+          "  -l, --limit <n>      number of results to return, default: all\n"
+          "      --load-complete  accepted for compatibility (the index always lives in HBM)\n"
+          "  -T, --threads <n>    accepted for compatibility (the search runs on the GPU)\n"
+          "      --gpus <n>       shard every index over n GPUs along the document axis\n"
+          "      --device <d>     first CUDA device to use, default: 0\n"
+          "      --batch <n>      FASTA records per GPU batch, default: 4096\n";
+}
+
+struct Batch {
+    std::vector<std::string> comments, queries;
+};
+
+void flush(cobs::Search& s, Batch& b, double threshold, unsigned num_results) {
+    if (b.queries.empty()) return;
+    std::vector<std::vector<cobs::SearchResult> > results;
+    s.search_batch(b.queries, results, threshold, num_results);
+    for (size_t i = 0; i < results.size(); ++i) {
+        std::cout << b.comments[i] << '\t' << results[i].size() << '\n';
+        for (const auto& res : results[i]) std::cout << res.doc_name << '\t' << res.score << '\n';
+    }
+    b.comments.clear();
+    b.queries.clear();
+}
+
+// same record splitting as process_query (src/cobs.cpp:425-462)
+void process_query(cobs::Search& s, double threshold, unsigned num_results,
+                   const std::string& query_line, const std::string& query_file, size_t batch) {
+    if (!query_line.empty()) {
+        std::vector<cobs::SearchResult> result;
+        s.search(query_line, result, threshold, num_results);
+        for (const auto& res : result) std::cout << res.doc_name << '\t' << res.score << '\n';
+    }
+    else if (!query_file.empty()) {
+        std::ifstream qf(query_file);
+        std::string line, query, comment;
+        Batch b;
+        auto push = [&] {
+            b.comments.push_back(comment);
+            b.queries.push_back(query);
+            if (b.queries.size() >= batch) flush(s, b, threshold, num_results);
+        };
+        while (std::getline(qf, line)) {
+            if (line.empty()) continue;
+            if (line[0] == '>' || line[0] == ';') {
+                if (!query.empty()) push();
+                line[0] = '*';
+                query.clear();
+                comment = line;
+            }
+            else {
+                query += line;
+            }
+        }
+        if (!query.empty()) push();
+        flush(s, b, threshold, num_results);
+    }
+    else {
+        cobs::die_with_message("Pass a verbatim query or a query file.");
+    }
+    s.timer().print("search");
+}
+
+int query(int argc, char** argv) {
+    std::vector<std::string> index_files;
+    std::string query, query_file;
+    double threshold = 0.8;
+    unsigned num_results = 0;
+    size_t batch = 4096;
+
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        auto value = [&](const char* name) -> std::string {
+            if (i + 1 >= argc) {
+                std::cerr << "Error: option " << name << " requires an argument!\n\n";
+                usage_query(std::cerr);
+                std::exit(-1);
+            }
+            return argv[++i];
+        };
+        if (a == "-i" || a == "--index") index_files.push_back(value("-i"));
+        else if (a == "-f" || a == "--file") query_file = value("-f");
+        else if (a == "-t" || a == "--threshold") threshold = std::atof(value("-t").c_str());
+        else if (a == "-l" || a == "--limit") num_results = unsigned(std::strtoul(value("-l").c_str(), nullptr, 10));
+        else if (a == "--load-complete") cobs::gopt_load_complete_index = true;
+        else if (a == "-T" || a == "--threads") cobs::gopt_threads = std::strtoul(value("-T").c_str(), nullptr, 10);
+        else if (a == "--gpus") cobs::gopt_gpus = unsigned(std::max(1, std::atoi(value("--gpus").c_str())));
+        else if (a == "--device") cobs::gopt_gpu_device = std::atoi(value("--device").c_str());
+        else if (a == "--batch") batch = std::max<size_t>(1, std::strtoul(value("--batch").c_str(), nullptr, 10));
+        else if (a == "-h" || a == "--help") {
+            usage_query(std::cout);
+            return -1;
+        }
+        else if (!a.empty() && a[0] == '-' && a.size() > 1) {
+            std::cerr << "Error: unknown option \"" << a << "\".\n\n";
+            usage_query(std::cerr);
+            return -1;
+        }
+        else if (query.empty()) query = a;
+        else {
+            std::cerr << "Error: unexpected extra argument \"" << a << "\".\n\n";
+            usage_query(std::cerr);
+            return -1;
+        }
+    }
+
+    std::vector<std::shared_ptr<cobs::IndexSearchFile> > indices;
+    for (auto& path : index_files) {
+        if (cobs::file_has_header<cobs::ClassicIndexHeader>(path))
+            indices.push_back(std::make_shared<cobs::ClassicIndexMMapSearchFile>(path));
+        else if (cobs::file_has_header<cobs::CompactIndexHeader>(path))
+            indices.push_back(std::make_shared<cobs::CompactIndexMMapSearchFile>(path));
+        else
+            cobs::die_with_message("Could not open index path \"" + path + "\"");
+    }
+    cobs::ClassicSearch s(indices);
+    process_query(s, threshold, num_results, query, query_file, batch);
+    return 0;
+}
+
+void usage(const char* prog) {
+    std::cout << "(Co)mpact (B)it-Sliced (S)ignature Index for Genome Search -- B200 query path\n\n"
+              << "Usage: " << prog << " <subtool> ...\n\n"
+              << "Available subtools:\n"
+              << "  query    query an index (classic or compact) on the GPU\n"
+              << "  version  print version\n\n"
+              << "Index construction and the other subtools of the reference are not part of\n"
+              << "this build; indices written by the reference are read as they are.\n";
+}
+
+} // namespace
+
+int main(int argc, char** argv) {
+    if (argc < 2) {
+        usage(argv[0]);
+        return 0;
+    }
+    const std::string tool = argv[1];
+    try {
+        if (tool == "query") return query(argc - 1, argv + 1);
+        if (tool == "version") {
+            std::cout << "COBS B200 query path, C ABI version 1" << std::endl;
+            return 0;
+        }
+    }
+    catch (std::exception& e) {
+        // reference: src/cobs.cpp:1070-1076
+        std::cerr << "EXCEPTION: " << e.what() << std::endl;
+        return -1;
+    }
+    std::cout << "Unknown subtool \"" << tool << "\"\n";
+    usage(argv[0]);
+    return 0;
+}

@@ -42,6 +42,8 @@ IndexSearchFile::IndexSearchFile(const fs::path& path, int kind) {
     page_size_ = info.page_size;
     num_hashes_ = info.num_hashes;
     counts_size_ = info.counts_size;
+    for (uint32_t p = 0; p < info.n_pages; ++p)
+        signature_sizes_.push_back(cobsgpu_index_signature_size(shards_[0], p));
     file_names_.resize(info.n_docs);
     for (uint32_t d = 0; d < info.n_docs; ++d) file_names_[d] = cobsgpu_index_doc_name(shards_[0], d);
 }
@@ -58,10 +60,6 @@ void IndexSearchFile::read_from_disk(
     size_t begin, size_t size, size_t buffer_size) {
     if (page_size_ != 1 || shards_.size() != 1)
         die_with_message("read_from_disk() is only kept for single-GPU classic indices");
-    // signature_size is not part of the public getters: recover it from the handle
-    cobsgpu_index_info info;
-    cobsgpu_index_get_info(shards_[0], &info);
-    if (signature_sizes_.empty()) die_with_message("read_from_disk(): signature size unknown");
     for (size_t i = 0; i < hashes.size(); ++i) {
         uint64_t row = hashes[i] % signature_sizes_[0];
         if (cobsgpu_debug_read_row(shards_[0], 0, row, begin, size, rows + i * buffer_size) != COBSGPU_OK)

@@ -135,6 +135,8 @@ int cobsgpu_index_open_file(const char* path, int device, uint32_t shard_index,
                             uint32_t shard_count, cobsgpu_index** out);
 void cobsgpu_index_close(cobsgpu_index* idx);
 int cobsgpu_index_get_info(const cobsgpu_index* idx, cobsgpu_index_info* out);
+/* rows of global page `page` (the header's signature_size; classic: page 0); 0 if out of range */
+uint64_t cobsgpu_index_signature_size(const cobsgpu_index* idx, uint32_t page);
 /* IndexSearchFile::file_names()[doc].c_str(); NULL for synthetic indices */
 const char* cobsgpu_index_doc_name(const cobsgpu_index* idx, uint32_t doc);
 

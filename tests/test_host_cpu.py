@@ -1,0 +1,36 @@
+"""CPU tests of the host-side C++ layer: binaries exist, usage text, and -- without a GPU --
+the query path fails loudly instead of falling back to the CPU."""
+import os
+import subprocess
+
+import pytest
+
+import cobs_b200
+from conftest import ROOT, golden_path
+
+COBS = os.path.join(ROOT, "build", "cobs")
+
+
+def test_binaries_built():
+    for f in ("cobs", "host_tests", "libcobs_b200.so"):
+        assert os.path.exists(os.path.join(ROOT, "build", f)), f
+
+
+def test_usage_and_version():
+    r = subprocess.run([COBS], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 0 and "query" in r.stdout
+    r = subprocess.run([COBS, "version"], stdout=subprocess.PIPE, text=True)
+    assert "C ABI version 1" in r.stdout
+    r = subprocess.run([COBS, "query", "--help"], stdout=subprocess.PIPE, text=True)
+    for flag in ("--index", "--file", "--threshold", "--limit", "--load-complete", "--threads"):
+        assert flag in r.stdout       # the reference's flags (src/cobs.cpp:474-505)
+    assert "default: 0.8" in r.stdout
+
+
+@pytest.mark.skipif(cobs_b200.lib().cobsgpu_device_count() > 0, reason="GPU present")
+def test_cli_without_gpu_fails_loudly():
+    r = subprocess.run([COBS, "query", "-i", golden_path("all160.cobs_classic"), "ACGT" * 10],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode != 0
+    assert "no CPU fallback" in r.stderr
+    assert r.stdout == ""
