@@ -30,7 +30,7 @@ endif
 build/libcobs_b200.so: $(HOST_SRCS) $(LIB) $(shell find cobs_b200/host/include -name '*.hpp' 2>/dev/null)
 	@mkdir -p build
 	$(CXX) $(HOST_FLAGS) -shared -o $@ $(HOST_SRCS) -Lcobs_b200/lib -lcobsgpu \
-	    -Wl,-rpath,'$$ORIGIN/../cobs_b200/lib'
+	    -Wl,-rpath,'$$ORIGIN/../cobs_b200/lib' -lpthread
 
 build/cobs: cobs_b200/host/cli/cobs_main.cpp build/libcobs_b200.so
 	$(CXX) $(HOST_FLAGS) -o $@ $< -Lbuild -lcobs_b200 -Lcobs_b200/lib -lcobsgpu \

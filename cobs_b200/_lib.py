@@ -114,8 +114,8 @@ SYMBOLS = {
                                               C.c_double, C.c_uint64, C.c_uint32, C.c_void_p,
                                               C.c_void_p, C.c_void_p]),
     "cobsgpu_merge_device": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
-                                       C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p,
-                                       C.c_void_p, C.c_void_p]),
+                                       C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint64,
+                                       C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cobsgpu_get_timers": (C.c_int, [C.c_void_p, C.POINTER(Timers)]),
     "cobsgpu_reset_timers": (C.c_int, [C.c_void_p]),
     "cobsgpu_debug_read_row": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64,

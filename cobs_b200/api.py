@@ -205,11 +205,13 @@ class GpuIndex:
 
 
 def merge_device(device, n_lists, nq, results_per_query, d_counts_ptr, d_keys_ptr, num_results,
-                 out_per_query, d_out_counts_ptr, d_out_keys_ptr, stream=0):
+                 out_per_query, d_out_counts_ptr, d_out_keys_ptr, stream=0,
+                 counts_list_stride=0, keys_list_stride=0):
+    """strides in elements (uint32 / uint64); 0 = densely packed lists"""
     _lib.check(_lib.lib().cobsgpu_merge_device(device, n_lists, nq, results_per_query,
-                                               d_counts_ptr, d_keys_ptr, num_results,
-                                               out_per_query, d_out_counts_ptr, d_out_keys_ptr,
-                                               stream))
+                                               d_counts_ptr, counts_list_stride, d_keys_ptr,
+                                               keys_list_stride, num_results, out_per_query,
+                                               d_out_counts_ptr, d_out_keys_ptr, stream))
 
 
 def decode_keys(keys):

@@ -162,7 +162,25 @@ struct cobsgpu_index {
     // execution state
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    DevBuf d_queries, d_qoff, d_koff, d_thr, d_hashes, d_flags, d_qlist;
+    DevBuf d_queries, d_meta, d_hashes, d_qlist;
+    // per-batch metadata travels as ONE block: [flags 2 x int | qoff | koff | thr], staged in a
+    // ring of pinned buffers so that the upload is truly asynchronous
+    static constexpr int META_RING = 4;
+    PinBuf h_meta[META_RING];
+    cudaEvent_t meta_ev[META_RING] = { nullptr, nullptr, nullptr, nullptr };
+    int meta_slot = 0;
+    size_t meta_qoff = 0, meta_koff = 0, meta_thr = 0;   // byte offsets inside d_meta
+    int* d_flags() const { return d_meta.as<int>(); }
+    uint64_t* d_qoff() const { return reinterpret_cast<uint64_t*>(d_meta.as<char>() + meta_qoff); }
+    uint32_t* d_koff() const { return reinterpret_cast<uint32_t*>(d_meta.as<char>() + meta_koff); }
+    uint32_t* d_thr() const { return reinterpret_cast<uint32_t*>(d_meta.as<char>() + meta_thr); }
+    // cached launch configuration of the score kernel per mode
+    struct ScoreCfg {
+        bool valid = false;
+        uint32_t n_stages = 0;
+        size_t smem = 0;
+        int occupancy = 0;
+    } score_cfg[3];
     DevBuf d_cand, d_scratch, d_cand_count, d_res_count, d_offsets, d_out_doc, d_out_score, d_dense;
     PinBuf h_stage, h_off, h_doc, h_score, h_counts, h_dense;
     // current batch (host copies)
@@ -191,6 +209,8 @@ struct cobsgpu_index {
             cudaEventDestroy(e.b);
         }
         for (auto e : ev_pool) cudaEventDestroy(e);
+        for (auto e : meta_ev)
+            if (e) cudaEventDestroy(e);
         if (d_arena) cudaFree(d_arena);
         if (d_tiles) cudaFree(d_tiles);
         if (d_seg) cudaFree(d_seg);
@@ -461,33 +481,38 @@ ScoreFn pick_score(uint32_t h, int mode) {
 void launch_score(cobsgpu_index* ix, ScoreParams sp, int mode, cudaStream_t st) {
     if (sp.nq_items == 0 || sp.n_tiles == 0) return;
     const uint32_t h = ix->num_hashes;
-    const uint32_t W = ix->ncw * 512;
-    const uint32_t stage = h * W;
-    // ring depth from the shared-memory budget: aim for 3 CTAs/SM, fall back to 2 or 1 when
-    // a stage (h row slices) is large
-    const size_t avail = ix->smem_optin;   // 227 KB on B200
-    uint32_t ns = 0;
-    for (int occ = 3; occ >= 1; --occ) {
-        const size_t budget = avail / occ - (occ > 1 ? 1024 : 0);
-        if (budget <= 1024 + stage) continue;
-        ns = static_cast<uint32_t>((budget - 1024) / stage);
-        if (ns >= 4 || occ == 1) break;
-    }
-    if (ns == 0) throw Err{ COBSGPU_ERR_INVALID_ARG, "num_hashes too large for shared memory" };
-    ns = std::min<uint32_t>(ns, 64);
-    sp.n_stages = ns;
-    const size_t smem = round_up<size_t>(ns * 16, 128) + static_cast<size_t>(ns) * stage;
     ScoreFn fn = pick_score(h, mode);
-    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     const int threads = static_cast<int>((ix->ncw + 1) * 32);
-    int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem));
-    if (occ < 1) throw Err{ COBSGPU_ERR_CUDA, "score kernel does not fit on an SM" };
+    cobsgpu_index::ScoreCfg& cfg = ix->score_cfg[mode];
+    if (!cfg.valid) {
+        const uint32_t W = ix->ncw * 512;
+        const uint32_t stage = h * W;
+        // ring depth from the shared-memory budget: aim for 3 CTAs/SM, fall back to 2 or 1
+        // when a stage (h row slices) is large
+        const size_t avail = ix->smem_optin;   // 227 KB on B200
+        uint32_t ns = 0;
+        for (int occ = 3; occ >= 1; --occ) {
+            const size_t budget = avail / occ - (occ > 1 ? 1024 : 0);
+            if (budget <= 1024 + stage) continue;
+            ns = static_cast<uint32_t>((budget - 1024) / stage);
+            if (ns >= 4 || occ == 1) break;
+        }
+        if (ns == 0) throw Err{ COBSGPU_ERR_INVALID_ARG, "num_hashes too large for shared memory" };
+        ns = std::min<uint32_t>(ns, 64);
+        cfg.n_stages = ns;
+        cfg.smem = round_up<size_t>(ns * 16, 128) + static_cast<size_t>(ns) * stage;
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(cfg.smem)));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.occupancy, fn, threads, cfg.smem));
+        if (cfg.occupancy < 1) throw Err{ COBSGPU_ERR_CUDA, "score kernel does not fit on an SM" };
+        cfg.valid = true;
+    }
+    sp.n_stages = cfg.n_stages;
     const uint64_t items = static_cast<uint64_t>(sp.nq_items) * sp.n_tiles;
     const uint32_t grid = static_cast<uint32_t>(
-        std::min<uint64_t>(items, static_cast<uint64_t>(occ) * ix->sm_count));
+        std::min<uint64_t>(items, static_cast<uint64_t>(cfg.occupancy) * ix->sm_count));
     PhaseScope ps(ix, PH_SCORE, st);
-    fn<<<grid, threads, smem, st>>>(sp);
+    fn<<<grid, threads, cfg.smem, st>>>(sp);
     CK(cudaGetLastError());
     ix->tm.kernel_launches++;
     ix->tm.score_launches++;
@@ -496,14 +521,8 @@ void launch_score(cobsgpu_index* ix, ScoreParams sp, int mode, cudaStream_t st) 
 // ---------------------------------------------------------------------------------------
 // batch preparation: host geometry, uploads, K1
 
-// flags buffer: [0] first query with an invalid base, [1] first query overflowing its
-// candidate slots
-void reset_flags(cobsgpu_index* ix, cudaStream_t st) {
-    ix->d_flags.ensure(2 * sizeof(int));
-    static const int init[2] = { INT_MAX, INT_MAX };
-    CK(cudaMemcpyAsync(ix->d_flags.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
-}
-
+// d_meta starts with two flags: [0] first query with an invalid base, [1] first query
+// overflowing its candidate slots (both INT_MAX when clear)
 // queries [q0, q1) of the caller's batch; `queries` is a host pointer unless dev_queries
 void prepare_batch(cobsgpu_index* ix, const char* queries, bool dev_queries,
                    const uint64_t* offsets, uint32_t q0, uint32_t q1, double threshold,
@@ -541,7 +560,6 @@ void prepare_batch(cobsgpu_index* ix, const char* queries, bool dev_queries,
     ix->b_total_kmers = static_cast<uint32_t>(kmers);
     const uint64_t blob_bytes = ix->b_qoff[nq];
 
-    reset_flags(ix, st);
     {
         PhaseScope ps(ix, PH_H2D, st);
         if (dev_queries) {
@@ -551,28 +569,44 @@ void prepare_batch(cobsgpu_index* ix, const char* queries, bool dev_queries,
             CK(cudaMemcpyAsync(ix->d_queries.p, queries + base, blob_bytes, cudaMemcpyHostToDevice, st));
             ix->b_dev_queries = ix->d_queries.as<char>();
         }
-        ix->d_qoff.ensure((nq + 1) * 8);
-        ix->d_koff.ensure((nq + 1) * 4);
-        ix->d_thr.ensure(std::max<size_t>(nq, 1) * 4);
-        CK(cudaMemcpyAsync(ix->d_qoff.p, ix->b_qoff.data(), (nq + 1) * 8, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ix->d_koff.p, ix->b_koff.data(), (nq + 1) * 4, cudaMemcpyHostToDevice, st));
-        if (nq) CK(cudaMemcpyAsync(ix->d_thr.p, ix->b_thr.data(), nq * 4, cudaMemcpyHostToDevice, st));
+        // one block, one copy: flags | qoff | koff | thr
+        ix->meta_qoff = 8;
+        ix->meta_koff = ix->meta_qoff + (static_cast<size_t>(nq) + 1) * 8;
+        ix->meta_thr = ix->meta_koff + round_up<size_t>((static_cast<size_t>(nq) + 1) * 4, 8);
+        const size_t meta_bytes = ix->meta_thr + std::max<size_t>(nq, 1) * 4;
+        ix->d_meta.ensure(meta_bytes);
+        const int slot = ix->meta_slot;
+        ix->meta_slot = (slot + 1) % cobsgpu_index::META_RING;
+        if (!ix->meta_ev[slot]) CK(cudaEventCreateWithFlags(&ix->meta_ev[slot], cudaEventDisableTiming));
+        else CK(cudaEventSynchronize(ix->meta_ev[slot]));   // previous upload from this slot done
+        ix->h_meta[slot].ensure(meta_bytes);
+        char* hm = ix->h_meta[slot].as<char>();
+        reinterpret_cast<int*>(hm)[0] = INT_MAX;
+        reinterpret_cast<int*>(hm)[1] = INT_MAX;
+        std::memcpy(hm + ix->meta_qoff, ix->b_qoff.data(), (static_cast<size_t>(nq) + 1) * 8);
+        std::memcpy(hm + ix->meta_koff, ix->b_koff.data(), (static_cast<size_t>(nq) + 1) * 4);
+        if (nq) std::memcpy(hm + ix->meta_thr, ix->b_thr.data(), static_cast<size_t>(nq) * 4);
+        CK(cudaMemcpyAsync(ix->d_meta.p, hm, meta_bytes, cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(ix->meta_ev[slot], st));
     }
     ix->d_hashes.ensure(std::max<uint64_t>(1, kmers) * ix->num_hashes * 8);
     if (kmers) {
         HashParams hp{};
         hp.queries = ix->b_dev_queries;
-        hp.qoff = ix->d_qoff.as<uint64_t>();
-        hp.koff = ix->d_koff.as<uint32_t>();
+        hp.qoff = ix->d_qoff();
+        hp.koff = ix->d_koff();
         hp.nq = nq;
         hp.total_kmers = ix->b_total_kmers;
         hp.k = k;
         hp.h = ix->num_hashes;
         hp.canonicalize = ix->canonicalize;
         hp.hashes = ix->d_hashes.as<uint64_t>();
-        hp.first_bad = ix->d_flags.as<int>();
+        hp.first_bad = ix->d_flags();
         PhaseScope ps(ix, PH_HASH, st);
-        hash_kmers_kernel<<<div_ceil<uint32_t>(ix->b_total_kmers, 128), 128, 0, st>>>(hp);
+        const uint32_t grid = div_ceil<uint32_t>(ix->b_total_kmers, 128);
+        // k = 31 is what COBS indices use in practice: k-mer bytes held in registers
+        if (k == 31) hash_kmers_kernel<31><<<grid, 128, 0, st>>>(hp);
+        else hash_kmers_kernel<0><<<grid, 128, 0, st>>>(hp);
         CK(cudaGetLastError());
         ix->tm.kernel_launches++;
     }
@@ -586,10 +620,10 @@ ScoreParams base_params(cobsgpu_index* ix, const uint32_t* d_qlist, uint32_t n_s
     sp.n_tiles = static_cast<uint32_t>(ix->tiles.size());
     sp.h = ix->num_hashes;
     sp.hashes = ix->d_hashes.as<uint64_t>();
-    sp.koff = ix->d_koff.as<uint32_t>();
+    sp.koff = ix->d_koff();
     sp.qlist = d_qlist;
     sp.nq_items = n_slots;
-    sp.thr = ix->d_thr.as<uint32_t>();
+    sp.thr = ix->d_thr();
     sp.dense_pitch = ix->dense_pitch;
     return sp;
 }
@@ -632,7 +666,7 @@ void run_pass(cobsgpu_index* ix, const uint32_t* d_qlist, uint32_t n_slots, uint
             dp.dense32 = sp.dense32;
             dp.dense_pitch = ix->dense_pitch;
             dp.qlist = d_qlist;
-            dp.thr = ix->d_thr.as<uint32_t>();
+            dp.thr = ix->d_thr();
             const uint32_t np = static_cast<uint32_t>(ix->pages.size());
             dp.seg_dense_off = ix->d_seg;
             dp.seg_n_real = ix->d_seg + np;
@@ -651,7 +685,7 @@ void run_pass(cobsgpu_index* ix, const uint32_t* d_qlist, uint32_t n_slots, uint
     }
     PhaseScope ps(ix, PH_SELECT, st);
     result_counts_kernel<<<div_ceil<uint32_t>(n_slots, 256), 256, 0, st>>>(
-        sp.cand_count, n_slots, cap, limit, ix->d_res_count.as<uint32_t>(), ix->d_flags.as<int>() + 1);
+        sp.cand_count, n_slots, cap, limit, ix->d_res_count.as<uint32_t>(), ix->d_flags() + 1);
     CK(cudaGetLastError());
     sort_small_kernel<<<n_slots, SORT_SMALL_THREADS, 0, st>>>(sp.cand, sp.cand_count, cap, 1);
     CK(cudaGetLastError());
@@ -744,7 +778,7 @@ void fetch_pass(cobsgpu_index* ix, const uint32_t* d_qlist, uint32_t n_slots, ui
 
 void check_bad_base(cobsgpu_index* ix, uint32_t q0, cudaStream_t st) {
     int flags[2];
-    CK(cudaMemcpyAsync(flags, ix->d_flags.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(flags, ix->d_flags(), sizeof(flags), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (flags[0] != INT_MAX)
         throw Err{ COBSGPU_ERR_INVALID_BASE,
@@ -1108,6 +1142,24 @@ int cobsgpu_search_batch_device(cobsgpu_index* ix, const char* d_queries, const 
                 throw Err{ COBSGPU_ERR_INVALID_ARG,
                            "device-resident path handles queries of at most 255 k-mers" };
         const uint32_t cap = std::max<uint32_t>(results_per_query, ix->max_candidates);
+        if (cap <= SORT_SMALL_MAX) {
+            // fused K3: count + sort + strided output in one launch
+            ix->d_cand.ensure(static_cast<uint64_t>(nq) * cap * 8);
+            ix->d_cand_count.ensure(nq * 4);
+            CK(cudaMemsetAsync(ix->d_cand_count.p, 0, nq * 4, st));
+            ScoreParams sp = base_params(ix, nullptr, nq);
+            sp.cand_count = ix->d_cand_count.as<uint32_t>();
+            sp.cand = ix->d_cand.as<uint64_t>();
+            sp.cap = cap;
+            launch_score(ix, sp, MODE_CAND, st);
+            PhaseScope ps(ix, PH_SELECT, st);
+            FinalizeParams fp{ sp.cand, sp.cand_count, cap, nq, num_results, d_keys, d_counts,
+                               results_per_query };
+            finalize_strided_kernel<<<div_ceil<uint32_t>(nq, FIN_WARPS), FIN_WARPS * 32, 0, st>>>(fp);
+            CK(cudaGetLastError());
+            ix->tm.kernel_launches++;
+            return;
+        }
         bool lis = false;
         run_pass(ix, nullptr, nq, cap, false, 255, num_results, &lis, st);
         PhaseScope ps(ix, PH_SELECT, st);
@@ -1128,7 +1180,8 @@ int cobsgpu_search_batch_device(cobsgpu_index* ix, const char* d_queries, const 
 }
 
 int cobsgpu_merge_device(int device, uint32_t n_lists, uint32_t nq, uint32_t results_per_query,
-                         const uint32_t* d_counts, const uint64_t* d_keys, uint64_t num_results,
+                         const uint32_t* d_counts, uint64_t counts_list_stride,
+                         const uint64_t* d_keys, uint64_t keys_list_stride, uint64_t num_results,
                          uint32_t out_per_query, uint32_t* d_out_counts, uint64_t* d_out_keys,
                          void* stream) {
     return guarded([&] {
@@ -1144,7 +1197,10 @@ int cobsgpu_merge_device(int device, uint32_t n_lists, uint32_t nq, uint32_t res
         const size_t smem = static_cast<size_t>(np2) * 8;
         CK(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
-        MergeParams mp{ d_counts, d_keys, n_lists, nq, results_per_query, num_results,
+        MergeParams mp{ d_counts, d_keys,
+                        counts_list_stride ? counts_list_stride : nq,
+                        keys_list_stride ? keys_list_stride : static_cast<uint64_t>(nq) * results_per_query,
+                        n_lists, nq, results_per_query, num_results,
                         out_per_query, d_out_counts, d_out_keys };
         merge_kernel<<<nq, 256, smem, static_cast<cudaStream_t>(stream)>>>(mp);
         CK(cudaGetLastError());

@@ -110,9 +110,12 @@ __host__ __device__ __forceinline__ uint8_t base_rev(uint8_t c) {
 }
 
 // Hashes of one k-mer at `s`.  Returns false when canonicalising and a non-ACGT base occurs.
-template <typename Emit>
-__host__ __device__ __forceinline__ bool hash_kmer(const uint8_t* s, uint32_t k, uint32_t h,
+// KT > 0 fixes the k-mer length at compile time (the bytes then live in registers and are
+// shared by the h seeds); KT == 0 takes it from `k_rt`.
+template <int KT, typename Emit>
+__host__ __device__ __forceinline__ bool hash_kmer(const uint8_t* s, uint32_t k_rt, uint32_t h,
                                                    uint32_t canonicalize, Emit emit) {
+    const uint32_t k = KT > 0 ? static_cast<uint32_t>(KT) : k_rt;
     if (!canonicalize) {
         for (uint32_t j = 0; j < h; ++j)
             emit(j, xxh::hash64([&](uint32_t i) { return s[i]; }, k, j));
@@ -121,26 +124,25 @@ __host__ __device__ __forceinline__ bool hash_kmer(const uint8_t* s, uint32_t k,
     // the lexicographically smaller of (k-mer, reverse complement): first differing
     // position from the outside in decides; a tie over the whole first half keeps the
     // forward strand (cobs/util/query.cpp:155-198)
-    bool reverse = false, good = true;
+    bool reverse = false, decided = false, good = true;
+#pragma unroll
     for (uint32_t i = 0; i < k / 2; ++i) {
-        uint8_t f = base_fwd(s[i]), r = base_rev(s[k - 1 - i]);
-        if (f != r) {
+        const uint8_t f = base_fwd(s[i]), r = base_rev(s[k - 1 - i]);
+        if (!decided && f != r) {
             reverse = f > r;
-            break;
+            decided = true;
         }
     }
+#pragma unroll
     for (uint32_t i = 0; i < k; ++i) good = good && base_fwd(s[i]) != 0;
     if (!good) return false;
-    if (reverse) {
-        for (uint32_t j = 0; j < h; ++j)
-            emit(j, xxh::hash64([&](uint32_t i) { return base_rev(s[k - 1 - i]); }, k, j));
-    } else {
-        for (uint32_t j = 0; j < h; ++j)
-            emit(j, xxh::hash64([&](uint32_t i) { return s[i]; }, k, j));
-    }
+    for (uint32_t j = 0; j < h; ++j)
+        emit(j, xxh::hash64([&](uint32_t i) { return reverse ? base_rev(s[k - 1 - i]) : s[i]; },
+                            k, j));
     return true;
 }
 
+template <int KT>
 __global__ void __launch_bounds__(128) hash_kmers_kernel(HashParams p) {
     uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= p.total_kmers) return;
@@ -155,8 +157,18 @@ __global__ void __launch_bounds__(128) hash_kmers_kernel(HashParams p) {
     uint32_t t = gid - p.koff[q];
     const uint8_t* s = reinterpret_cast<const uint8_t*>(p.queries) + p.qoff[q] + t;
     uint64_t* out = p.hashes + static_cast<uint64_t>(gid) * p.h;
-    bool good = hash_kmer(s, p.k, p.h, p.canonicalize,
-                          [&](uint32_t j, uint64_t v) { out[j] = v; });
+    bool good;
+    if (KT > 0) {
+        // stage the bytes in registers once; the canonical form and all h seeds reuse them
+        uint8_t b[KT > 0 ? KT : 1];
+#pragma unroll
+        for (int i = 0; i < KT; ++i) b[i] = s[i];
+        good = hash_kmer<KT>(b, p.k, p.h, p.canonicalize,
+                             [&](uint32_t j, uint64_t v) { out[j] = v; });
+    } else {
+        good = hash_kmer<0>(s, p.k, p.h, p.canonicalize,
+                            [&](uint32_t j, uint64_t v) { out[j] = v; });
+    }
     if (!good) atomicMin(p.first_bad, static_cast<int>(q));
 }
 

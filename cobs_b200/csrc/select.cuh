@@ -298,10 +298,76 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherParams p) {
     }
 }
 
+// Fused K3 for the device-resident path (cap <= SORT_SMALL_MAX): result count + sort + strided
+// output in ONE kernel.  A CTA owns FIN_WARPS queries: lists of <= 32 candidates (the common
+// case at the CLI's default threshold) are sorted by one warp with shuffles; longer ones by the
+// whole CTA in shared memory afterwards.
+static constexpr uint32_t FIN_WARPS = 8;
+
+struct FinalizeParams {
+    const uint64_t* cand;
+    const uint32_t* cand_count;
+    uint32_t cap;
+    uint32_t nq;
+    uint64_t limit;
+    uint64_t* out_keys;     // [nq * stride]
+    uint32_t* out_counts;   // [nq]; 0xFFFFFFFF when the candidates overflowed `cap`
+    uint32_t stride;
+};
+
+__global__ void __launch_bounds__(FIN_WARPS * 32) finalize_strided_kernel(FinalizeParams p) {
+    __shared__ uint64_t s[SORT_SMALL_MAX];
+    __shared__ uint32_t big_n[FIN_WARPS];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t q = blockIdx.x * FIN_WARPS + warp;
+    uint32_t n = 0, r = 0;
+    if (lane == 0) big_n[warp] = 0;
+    if (q < p.nq) {
+        const uint32_t c = p.cand_count[q];
+        n = c < p.cap ? c : p.cap;
+        r = (p.limit != 0 && n > p.limit) ? static_cast<uint32_t>(p.limit) : n;
+        if (r > p.stride) r = p.stride;
+        if (lane == 0) p.out_counts[q] = c > p.cap ? 0xFFFFFFFFu : r;
+        if (c > p.cap) n = 0;   // flagged: the list would be incomplete
+        if (n > 32) {
+            if (lane == 0) big_n[warp] = n;
+        } else if (n > 0) {
+            uint64_t key = lane < n ? p.cand[static_cast<uint64_t>(q) * p.cap + lane] : KEY_PAD;
+#pragma unroll
+            for (uint32_t k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+                for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                    const uint64_t other = __shfl_xor_sync(0xFFFFFFFFu, key, j);
+                    const bool take_min = ((lane & j) == 0) == ((lane & k) == 0);
+                    key = take_min ? (key < other ? key : other) : (key > other ? key : other);
+                }
+            }
+            if (lane < r) p.out_keys[static_cast<uint64_t>(q) * p.stride + lane] = key;
+        }
+    }
+    __syncthreads();
+    for (uint32_t w = 0; w < FIN_WARPS; ++w) {
+        const uint32_t bn = big_n[w];
+        if (bn == 0) continue;   // uniform across the CTA
+        const uint32_t bq = blockIdx.x * FIN_WARPS + w;
+        const uint64_t* keys = p.cand + static_cast<uint64_t>(bq) * p.cap;
+        const uint32_t np2 = next_pow2(bn);
+        for (uint32_t i = threadIdx.x; i < np2; i += blockDim.x) s[i] = i < bn ? keys[i] : KEY_PAD;
+        __syncthreads();
+        block_bitonic_sort(s, np2);
+        uint32_t br = (p.limit != 0 && bn > p.limit) ? static_cast<uint32_t>(p.limit) : bn;
+        if (br > p.stride) br = p.stride;
+        for (uint32_t i = threadIdx.x; i < br; i += blockDim.x)
+            p.out_keys[static_cast<uint64_t>(bq) * p.stride + i] = s[i];
+        __syncthreads();
+    }
+}
+
 // shard merge: per query concatenate n_lists sorted lists, sort, keep the first `limit`.
 struct MergeParams {
-    const uint32_t* counts;   // [n_lists][nq]
-    const uint64_t* keys;     // [n_lists][nq][stride]
+    const uint32_t* counts;   // list l at counts + l * counts_list_stride: [nq]
+    const uint64_t* keys;     // list l at keys + l * keys_list_stride: [nq][stride]
+    uint64_t counts_list_stride, keys_list_stride;   // in elements
     uint32_t n_lists, nq, stride;
     uint64_t limit;
     uint32_t out_stride;
@@ -316,7 +382,7 @@ __global__ void __launch_bounds__(256) merge_kernel(MergeParams p) {
     if (threadIdx.x == 0) {
         uint32_t t = 0, o = 0;
         for (uint32_t l = 0; l < p.n_lists; ++l) {
-            const uint32_t c = p.counts[static_cast<uint64_t>(l) * p.nq + q];
+            const uint32_t c = p.counts[l * p.counts_list_stride + q];
             if (c == 0xFFFFFFFFu) o = 1;   // a shard overflowed its candidate slots
             else t += c < p.stride ? c : p.stride;
         }
@@ -332,9 +398,9 @@ __global__ void __launch_bounds__(256) merge_kernel(MergeParams p) {
     // lists are short; every thread walks the list table
     uint32_t start = 0;
     for (uint32_t l = 0; l < p.n_lists; ++l) {
-        uint32_t c = p.counts[static_cast<uint64_t>(l) * p.nq + q];
+        uint32_t c = p.counts[l * p.counts_list_stride + q];
         if (c > p.stride) c = p.stride;
-        const uint64_t* src = p.keys + (static_cast<uint64_t>(l) * p.nq + q) * p.stride;
+        const uint64_t* src = p.keys + l * p.keys_list_stride + static_cast<uint64_t>(q) * p.stride;
         for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) ms[start + i] = src[i];
         start += c;
     }

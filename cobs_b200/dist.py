@@ -28,6 +28,7 @@ class ShardedSearch:
         self.world = world
         self.rpq = results_per_query
         self.group = group
+        self._bufs = {}
 
     # -- hooks (overridden by the CPU/gloo protocol test) -------------------------------
     def _local_search(self, d_queries, off, threshold, num_results, counts, keys):
@@ -40,47 +41,69 @@ class ShardedSearch:
         nq = all_counts.shape[1]
         api.merge_device(all_counts.device.index or 0, self.world, nq, self.rpq,
                          all_counts.data_ptr(), all_keys.data_ptr(), num_results,
-                         out_keys.shape[1], out_counts.data_ptr(), out_keys.data_ptr(), stream)
+                         out_keys.shape[1], out_counts.data_ptr(), out_keys.data_ptr(), stream,
+                         counts_list_stride=all_counts.stride(0),
+                         keys_list_stride=all_keys.stride(0))
 
     # ------------------------------------------------------------------------------------
     def out_per_query(self, num_results):
         cap = self.rpq * self.world
         return cap if num_results == 0 else min(num_results, cap)
 
+    def _buffers(self, nq, k, dev):
+        """Per (nq, k) work buffers, allocated once.  A rank's result block is ONE int64
+        tensor [counts (nq x int32, padded) | keys (nq x rpq)], so a single all-gather moves
+        everything."""
+        key = (nq, k, str(dev))
+        b = self._bufs.get(key)
+        if b is None:
+            h = (nq + 1) // 2                      # int64 words holding the int32 counts
+            L = h + nq * self.rpq
+            block = torch.zeros(L, dtype=torch.int64, device=dev)
+            gathered = torch.zeros(self.world * L, dtype=torch.int64, device=dev)
+            g2 = gathered.view(self.world, L)
+            b = {
+                "block": block,
+                "counts": block[:h].view(torch.int32)[:nq],
+                "keys": block[h:].view(nq, self.rpq),
+                "gathered": gathered,
+                "all_counts": g2[:, :h].view(torch.int32)[:, :nq],
+                "all_keys": g2[:, h:].view(self.world, nq, self.rpq),
+                "out_counts": torch.zeros(nq, dtype=torch.int32, device=dev),
+                "out_keys": torch.zeros((nq, k), dtype=torch.int64, device=dev),
+            }
+            self._bufs[key] = b
+        return b
+
     def search_device(self, d_queries, off, threshold, num_results):
         """d_queries: uint8 tensor on this rank's device holding the packed batch; off: host
-        uint64[nq+1].  Returns (counts int32[nq], keys int64[nq, out_per_query]) on the device;
+        uint64[nq+1].  Returns (counts int32[nq], keys int64[nq, out_per_query]) on the device
+        (buffers owned by this object, overwritten by the next call with the same shape);
         key = (~score << 32) | global_doc, ascending == (score desc, doc asc); a count of
         0xFFFFFFFF (as uint32) flags a query whose candidates overflowed on some rank."""
         nq = len(off) - 1
-        dev = d_queries.device
-        counts = torch.empty(nq, dtype=torch.int32, device=dev)
-        keys = torch.empty((nq, self.rpq), dtype=torch.int64, device=dev)
-        self._local_search(d_queries, off, threshold, num_results, counts, keys)
-        if self.world == 1:
-            k = self.out_per_query(num_results)
-            return counts, keys[:, :k]
-        # rank-major concatenation along dim 0 (the layout both NCCL and gloo accept)
-        flat_counts = torch.empty(self.world * nq, dtype=torch.int32, device=dev)
-        flat_keys = torch.empty((self.world * nq, self.rpq), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(flat_counts, counts, group=self.group)
-        dist.all_gather_into_tensor(flat_keys, keys, group=self.group)
-        all_counts = flat_counts.view(self.world, nq)
-        all_keys = flat_keys.view(self.world, nq, self.rpq)
         k = self.out_per_query(num_results)
-        out_counts = torch.empty(nq, dtype=torch.int32, device=dev)
-        out_keys = torch.empty((nq, k), dtype=torch.int64, device=dev)
-        self._merge(all_counts, all_keys, num_results, out_counts, out_keys)
-        return out_counts, out_keys
+        b = self._buffers(nq, k, d_queries.device)
+        self._local_search(d_queries, off, threshold, num_results, b["counts"], b["keys"])
+        if self.world == 1:
+            return b["counts"], b["keys"][:, :k]
+        # rank-major concatenation along dim 0 (the layout both NCCL and gloo accept)
+        dist.all_gather_into_tensor(b["gathered"], b["block"], group=self.group)
+        self._merge(b["all_counts"], b["all_keys"], num_results, b["out_counts"], b["out_keys"])
+        return b["out_counts"], b["out_keys"]
 
     def search_host(self, h_queries, off, threshold, num_results):
         """end-to-end variant: h_queries is a (pinned) host uint8 tensor; returns numpy
-        (counts uint32[nq], keys uint64[nq, k]) on the host."""
+        (counts uint32[nq], keys uint64[nq, kmax]) on the host, kmax = longest result list."""
         dev = torch.device("cuda", torch.cuda.current_device())
         d_q = h_queries.to(dev, non_blocking=True)
         counts, keys = self.search_device(d_q, off, threshold, num_results)
         c = counts.cpu().numpy().view(np.uint32)
-        k = keys.cpu().numpy().view(np.uint64)
+        valid = c[c != OVERFLOW]
+        kmax = int(valid.max()) if valid.size else 0
+        kmax = min(kmax, keys.shape[1])
+        k = keys[:, :kmax].contiguous().cpu().numpy().view(np.uint64) if kmax else \
+            np.zeros((len(c), 0), dtype=np.uint64)
         return c, k
 
 

@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <thread>
 #include <tuple>
 
 namespace cobs {
@@ -66,28 +67,55 @@ void run_index(
         sub.append(blob, offsets[ids[i]], offsets[ids[i] + 1] - offsets[ids[i]]);
         off[i + 1] = sub.size();
     }
-    for (cobsgpu_index* shard : index.gpu_shards()) {
-        cobsgpu_set_option(shard, "timing", 1);
-        cobsgpu_reset_timers(shard);
+    // one host thread per document shard (= per GPU); each handle has its own stream and buffers
+    const auto& shards = index.gpu_shards();
+    struct ShardOut {
+        int rc = COBSGPU_OK;
+        std::string err;
+        std::vector<uint64_t> off;
+        std::vector<uint32_t> doc, score;
+        cobsgpu_timers tm{};
+    };
+    std::vector<ShardOut> outs(shards.size());
+    auto work = [&](size_t s) {
+        ShardOut& o = outs[s];
+        cobsgpu_set_option(shards[s], "timing", 1);
+        cobsgpu_reset_timers(shards[s]);
         cobsgpu_result res;
-        int rc = cobsgpu_search_batch(shard, sub.data(), off.data(), uint32_t(ids.size()),
-                                      threshold, limit, &res);
-        if (rc == COBSGPU_ERR_QUERY_TOO_SHORT) exit_error(cobsgpu_last_error());
-        if (rc == COBSGPU_ERR_INVALID_BASE)
+        o.rc = cobsgpu_search_batch(shards[s], sub.data(), off.data(), uint32_t(ids.size()),
+                                    threshold, limit, &res);
+        if (o.rc != COBSGPU_OK) {
+            o.err = cobsgpu_last_error();   // thread-local in the library: read it here
+            return;
+        }
+        o.off.assign(res.offsets, res.offsets + ids.size() + 1);
+        o.doc.assign(res.doc, res.doc + o.off.back());
+        o.score.assign(res.score, res.score + o.off.back());
+        cobsgpu_get_timers(shards[s], &o.tm);
+    };
+    if (shards.size() == 1) {
+        work(0);
+    }
+    else {
+        std::vector<std::thread> threads;
+        for (size_t s = 0; s < shards.size(); ++s) threads.emplace_back(work, s);
+        for (auto& t : threads) t.join();
+    }
+    for (ShardOut& o : outs) {
+        if (o.rc == COBSGPU_ERR_QUERY_TOO_SHORT) exit_error(o.err);
+        if (o.rc == COBSGPU_ERR_INVALID_BASE)
             die_with_message("Invalid DNA base pair in query string. Only ACGT are allowed.");
-        if (rc != COBSGPU_OK) die_with_message(std::string("GPU search failed: ") + cobsgpu_last_error());
+        if (o.rc != COBSGPU_OK) die_with_message("GPU search failed: " + o.err);
         for (size_t i = 0; i < ids.size(); ++i) {
             std::vector<Entry>& dst = out[ids[i]];
-            for (uint64_t e = res.offsets[i]; e < res.offsets[i + 1]; ++e)
-                dst.push_back(Entry { res.score[e], file_num, res.doc[e] });
+            for (uint64_t e = o.off[i]; e < o.off[i + 1]; ++e)
+                dst.push_back(Entry { o.score[e], file_num, o.doc[e] });
         }
-        cobsgpu_timers tm;
-        cobsgpu_get_timers(shard, &tm);
-        timer.add("hashes", tm.hashes_ms * 1e-3);
-        timer.add("io", (tm.h2d_ms + tm.d2h_ms) * 1e-3);
-        timer.add("and rows", tm.score_ms * 1e-3);   // gather + AND + add are one fused kernel
+        timer.add("hashes", o.tm.hashes_ms * 1e-3);
+        timer.add("io", (o.tm.h2d_ms + o.tm.d2h_ms) * 1e-3);
+        timer.add("and rows", o.tm.score_ms * 1e-3);   // gather + AND + add are one fused kernel
         timer.add("add rows", 0.0);
-        timer.add("sort results", tm.select_ms * 1e-3);
+        timer.add("sort results", o.tm.select_ms * 1e-3);
     }
 }
 

@@ -187,13 +187,16 @@ int cobsgpu_search_batch_device(cobsgpu_index* idx, const char* d_queries,
                                 uint64_t* d_keys, void* stream);
 
 /* K3 merge for document-sharded indices: n_lists per-query lists (e.g. the all-gathered
- * outputs of cobsgpu_search_batch_device from every rank, laid out
- * [n_lists][nq][results_per_query]) are merged into one ordered list per query of at most
- * num_results (0 = results_per_query * n_lists capped at out_per_query) entries.
- * Device pointers; asynchronous on `stream`. */
+ * outputs of cobsgpu_search_batch_device from every rank) are merged into one ordered list
+ * per query of at most min(num_results or all, out_per_query) entries.  List l has its counts
+ * [nq] at d_counts + l * counts_list_stride (uint32 elements) and its keys
+ * [nq][results_per_query] at d_keys + l * keys_list_stride (uint64 elements); a stride of 0
+ * means densely packed ([n_lists][nq] / [n_lists][nq][results_per_query]).  A count of
+ * UINT32_MAX in any list propagates to the output.  Device pointers; asynchronous on `stream`. */
 int cobsgpu_merge_device(int device, uint32_t n_lists, uint32_t nq,
                          uint32_t results_per_query, const uint32_t* d_counts,
-                         const uint64_t* d_keys, uint64_t num_results,
+                         uint64_t counts_list_stride, const uint64_t* d_keys,
+                         uint64_t keys_list_stride, uint64_t num_results,
                          uint32_t out_per_query, uint32_t* d_out_counts,
                          uint64_t* d_out_keys, void* stream);
 
