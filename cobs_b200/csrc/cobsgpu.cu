@@ -535,6 +535,8 @@ void prepare_batch(cobsgpu_index* ix, const char* queries, bool dev_queries,
     ix->b_thr.resize(nq);
     const uint64_t base = offsets[q0];
     uint64_t kmers = 0;
+    uint32_t uniform_T = 0;
+    bool uniform = true;
     for (uint32_t i = 0; i < nq; ++i) {
         if (offsets[q0 + i + 1] < offsets[q0 + i])
             throw Err{ COBSGPU_ERR_INVALID_ARG, "query offsets must be non-decreasing" };
@@ -549,12 +551,15 @@ void prepare_batch(cobsgpu_index* ix, const char* queries, bool dev_queries,
         ix->b_qoff[i] = offsets[q0 + i] - base;
         ix->b_koff[i] = static_cast<uint32_t>(kmers);
         kmers += T;
+        if (i == 0) uniform_T = static_cast<uint32_t>(T);
+        else if (T != uniform_T) uniform = false;
         // thresholds[i] = ceil(threshold * num_terms) in double (classic_search.cpp:444-449)
         double th = std::ceil(threshold * static_cast<double>(T));
         ix->b_thr[i] = th <= 0.0 ? 0u : (th >= 4294967295.0 ? 0xFFFFFFFFu : static_cast<uint32_t>(th));
     }
     if (kmers > 0x7FFFFFFFull)
         throw Err{ COBSGPU_ERR_INVALID_ARG, "batch holds more than 2^31 k-mers" };
+    if (!uniform) uniform_T = 0;
     ix->b_qoff[nq] = offsets[q1] - base;
     ix->b_koff[nq] = static_cast<uint32_t>(kmers);
     ix->b_total_kmers = static_cast<uint32_t>(kmers);
@@ -597,6 +602,7 @@ void prepare_batch(cobsgpu_index* ix, const char* queries, bool dev_queries,
         hp.koff = ix->d_koff();
         hp.nq = nq;
         hp.total_kmers = ix->b_total_kmers;
+        hp.uniform_T = uniform_T;
         hp.k = k;
         hp.h = ix->num_hashes;
         hp.canonicalize = ix->canonicalize;
