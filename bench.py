@@ -304,6 +304,7 @@ def run_ours(args):
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     tm = index.timers()
     score_ms = torch.tensor([tm["score_ms"] / max(tm["score_launches"], 1)], device=dev)
+    phases = {k: tm[k] / args.steps for k in ("hashes_ms", "score_ms", "select_ms", "h2d_ms")}
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(score_ms, op=dist.ReduceOp.MAX)
@@ -379,6 +380,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
+            "phases_ms_per_step_rank0": phases,
             "clocks": clocks,
         }
         if cpu is not None:

@@ -148,6 +148,7 @@ struct cobsgpu_index {
     uint32_t shard_doc_begin = 0, shard_doc_end = 0;
     uint64_t bytes_per_kmer = 0;
     uint32_t* d_seg = nullptr;    // [3][n_local_pages]: dense_off, n_real, doc_base
+    unsigned long long* d_work = nullptr;   // score kernel work counters (zero between launches)
 
     // device properties
     int sm_count = 0;
@@ -214,6 +215,7 @@ struct cobsgpu_index {
         if (d_arena) cudaFree(d_arena);
         if (d_tiles) cudaFree(d_tiles);
         if (d_seg) cudaFree(d_seg);
+        if (d_work) cudaFree(d_work);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
 };
@@ -452,6 +454,8 @@ void open_common(cobsgpu_index* ix, const std::vector<uint64_t>& sig,
         CK(cudaStreamSynchronize(ix->stream));
     }
     build_tiles(ix);
+    CK(cudaMalloc(reinterpret_cast<void**>(&ix->d_work), 16));
+    CK(cudaMemset(ix->d_work, 0, 16));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -493,14 +497,14 @@ void launch_score(cobsgpu_index* ix, ScoreParams sp, int mode, cudaStream_t st) 
         uint32_t ns = 0;
         for (int occ = 3; occ >= 1; --occ) {
             const size_t budget = avail / occ - (occ > 1 ? 1024 : 0);
-            if (budget <= 1024 + stage) continue;
-            ns = static_cast<uint32_t>((budget - 1024) / stage);
+            if (budget <= 2048 + stage) continue;
+            ns = static_cast<uint32_t>((budget - 2048) / stage);
             if (ns >= 4 || occ == 1) break;
         }
         if (ns == 0) throw Err{ COBSGPU_ERR_INVALID_ARG, "num_hashes too large for shared memory" };
         ns = std::min<uint32_t>(ns, 64);
         cfg.n_stages = ns;
-        cfg.smem = round_up<size_t>(ns * 16, 128) + static_cast<size_t>(ns) * stage;
+        cfg.smem = score_smem_header(ns) + static_cast<size_t>(ns) * stage;
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(cfg.smem)));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.occupancy, fn, threads, cfg.smem));
@@ -631,6 +635,7 @@ ScoreParams base_params(cobsgpu_index* ix, const uint32_t* d_qlist, uint32_t n_s
     sp.nq_items = n_slots;
     sp.thr = ix->d_thr();
     sp.dense_pitch = ix->dense_pitch;
+    sp.work = ix->d_work;
     return sp;
 }
 

@@ -9,7 +9,10 @@
 //
 // Design (B200, HBM-bound integer work, no tensor cores):
 //   * work item = (query, column tile); a tile is <= W = 512*NCW contiguous bytes of a
-//     signature row (4096*NCW documents).  Persistent CTAs stride over the items.
+//     signature row (4096*NCW documents).  Persistent CTAs pull items from a global atomic
+//     counter (the producer warp fetches, consumers follow through a 2-slot shared queue), so
+//     no CTA is ever more than one item behind at the end: a straggler CTA alone is
+//     latency-bound (~37 GB/s), which made static striding cost ~0.1 ms per launch.
 //   * one PRODUCER warp per CTA turns raw hashes into row addresses (hash % signature_size,
 //     one modulus per page) and streams the h row slices of every k-mer into a shared-memory
 //     ring with 1-D TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP);
@@ -62,7 +65,16 @@ struct ScoreParams {
     uint8_t* dense8;          // [nq_items * dense_pitch]
     uint32_t* dense32;        // [nq_items * dense_pitch] (zero-initialised)
     uint64_t dense_pitch;     // columns per slot, multiple of 128
+    // dynamic work distribution: [0] next item, [1] CTAs finished (both zero between launches;
+    // the last CTA to finish resets them)
+    unsigned long long* work;
 };
+
+// shared-memory header of a CTA: full[NS] + empty[NS] + item-queue barriers and slots
+__host__ __device__ constexpr uint32_t score_smem_header(uint32_t ns) {
+    return ((2 * ns + 6) * 8 + 127) / 128 * 128;
+}
+static constexpr uint32_t SCORE_ITEM_Q = 2;   // item ids the producer may run ahead
 
 static constexpr int SCORE_MAX_THREADS = 160;   // 4 consumer warps + 1 producer warp
 static constexpr int SCORE_PLANES = 8;          // counts up to 255 between flushes
@@ -122,7 +134,10 @@ __global__ void __launch_bounds__(SCORE_MAX_THREADS, 3) score_kernel(const Score
     const uint32_t stage_bytes = h * W;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty = full + NS;
-    uint8_t* data = smem + round_up<uint32_t>(NS * 16, 128);
+    uint64_t* iq_full = empty + NS;                 // item queue: slot published by the producer
+    uint64_t* iq_empty = iq_full + SCORE_ITEM_Q;    // slot read by every consumer warp
+    volatile uint64_t* item_q = iq_empty + SCORE_ITEM_Q;
+    uint8_t* data = smem + score_smem_header(NS);
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -130,12 +145,17 @@ __global__ void __launch_bounds__(SCORE_MAX_THREADS, 3) score_kernel(const Score
             mbar_init(&full[s], h);      // one arrive.expect_tx per row slice
             mbar_init(&empty[s], ncw);   // one arrive per consumer warp
         }
+        for (uint32_t s = 0; s < SCORE_ITEM_Q; ++s) {
+            mbar_init(&iq_full[s], 1);
+            mbar_init(&iq_empty[s], ncw);
+        }
         mbar_fence_init();
     }
     __syncthreads();
 
     const uint64_t n_items = static_cast<uint64_t>(p.nq_items) * p.n_tiles;
     uint32_t s = 0, par = 0;   // ring position / phase parity, advanced identically by both roles
+    uint32_t iq = 0, iq_par = 0;   // item-queue position / parity, likewise
 
     if (warp == ncw) {
         // ------------------------------ producer warp ------------------------------
@@ -144,7 +164,21 @@ __global__ void __launch_bounds__(SCORE_MAX_THREADS, 3) score_kernel(const Score
         const uint32_t my_k = lane / h, my_j = lane - my_k * h;
         const bool lane_used = my_k < kpr;
         const uint64_t policy = l2_policy_evict_first();
-        for (uint64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        for (;;) {
+            // next item from the global counter, published to the consumer warps
+            unsigned long long item = 0;
+            if (lane == 0) {
+                mbar_wait(&iq_empty[iq], iq_par ^ 1);
+                item = atomicAdd(p.work, 1ull);
+                item_q[iq] = item;
+                mbar_arrive(&iq_full[iq]);
+            }
+            item = __shfl_sync(0xFFFFFFFFu, item, 0);
+            if (++iq == SCORE_ITEM_Q) {
+                iq = 0;
+                iq_par ^= 1;
+            }
+            if (item >= n_items) break;
             const uint32_t qi = static_cast<uint32_t>(item / p.n_tiles);
             const uint32_t tile = static_cast<uint32_t>(item - static_cast<uint64_t>(qi) * p.n_tiles);
             const uint32_t q = p.qlist ? p.qlist[qi] : qi;
@@ -175,12 +209,29 @@ __global__ void __launch_bounds__(SCORE_MAX_THREADS, 3) score_kernel(const Score
                 __syncwarp();
             }
         }
+        // the last CTA to run out of work re-arms the counters for the next launch
+        if (lane == 0) {
+            const unsigned long long done = atomicAdd(p.work + 1, 1ull);
+            if (done == gridDim.x - 1) {
+                p.work[0] = 0;
+                p.work[1] = 0;
+            }
+        }
         return;
     }
 
     // -------------------------------- consumer warps --------------------------------
     const uint8_t* my = data + threadIdx.x * 16;
-    for (uint64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (;;) {
+        mbar_wait(&iq_full[iq], iq_par);
+        const uint64_t item = item_q[iq];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&iq_empty[iq]);
+        if (++iq == SCORE_ITEM_Q) {
+            iq = 0;
+            iq_par ^= 1;
+        }
+        if (item >= n_items) break;
         const uint32_t qi = static_cast<uint32_t>(item / p.n_tiles);
         const uint32_t tile = static_cast<uint32_t>(item - static_cast<uint64_t>(qi) * p.n_tiles);
         const uint32_t q = p.qlist ? p.qlist[qi] : qi;
