@@ -262,7 +262,7 @@ def run_ours(args):
     index.set_option("max_batch", max(nq, 1))
     info = index.info
     rpq = args.results_per_query
-    sharded = ShardedSearch(index, rank, world, rpq)
+    sharded = ShardedSearch(index, rank, world, rpq, overlap=not args.no_overlap)
 
     # bytes per k-mer of the WHOLE index (h * ceil(N/8), unpadded reference layout)
     if cfg["kind"] == 0:
@@ -284,8 +284,14 @@ def run_ours(args):
     # ---- leg 1: device-resident inputs ("value") ----
     d_batches = [p.to(dev) for p in pinned]
     torch.cuda.synchronize()
+    if not args.no_overlap:
+        # steps are independent batches: upload + K1 of step i+1 (and, for N > 1, the exchange
+        # of step i) overlap the score kernel of the neighbouring step
+        index.set_option("prefetch", 1)
+        index.set_option("inputs_ready", 1)     # every batch is already resident in HBM
     for i in range(args.warmup):
         sharded.search_device(d_batches[i], off, THRESHOLD, 0)
+    sharded.join()
     barrier()
     index.set_option("timing", 1)
     index.timers(reset=True)
@@ -298,6 +304,7 @@ def run_ours(args):
     last = None
     for i in range(args.steps):
         last = sharded.search_device(d_batches[args.warmup + i], off, THRESHOLD, 0)
+    sharded.join()
     ev1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -313,6 +320,7 @@ def run_ours(args):
     value = kmers_per_step * args.steps / (ms_total * 1e-3)
     launches = tm["kernel_launches"] + (args.steps if world > 1 else 0)
     index.set_option("timing", 0)
+    index.set_option("inputs_ready", 0)     # the e2e leg uploads its queries itself
     n_results = int((last[0].cpu().numpy().view(np.uint32) % 0xFFFFFFFF).sum())
 
     # ---- leg 2: end to end from host buffers through the public API ("e2e") ----
@@ -405,6 +413,8 @@ def main():
     ap.add_argument("--ref-queries", type=int, default=400,
                     help="queries per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="disable the cross-step pipelining (K1 prefetch, side-stream exchange)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

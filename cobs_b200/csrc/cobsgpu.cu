@@ -163,7 +163,16 @@ struct cobsgpu_index {
     // execution state
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    DevBuf d_queries, d_meta, d_hashes, d_qlist;
+    DevBuf d_queries, d_meta_[2], d_hashes_[2], d_qlist;
+    // two sets of {metadata, hashes}: with "prefetch" on, the device-resident path runs the
+    // upload + K1 of call i+1 on pre_stream while K2 of call i still reads set i
+    int cur = 0;
+    DevBuf& meta() { return d_meta_[cur]; }
+    DevBuf& hashes() { return d_hashes_[cur]; }
+    bool prefetch = false, inputs_ready = false;
+    cudaStream_t pre_stream = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_k1[2] = { nullptr, nullptr }, ev_k2[2] = { nullptr, nullptr };
+    bool ev_k2_valid[2] = { false, false };
     // per-batch metadata travels as ONE block: [flags 2 x int | qoff | koff | thr], staged in a
     // ring of pinned buffers so that the upload is truly asynchronous
     static constexpr int META_RING = 4;
@@ -171,10 +180,10 @@ struct cobsgpu_index {
     cudaEvent_t meta_ev[META_RING] = { nullptr, nullptr, nullptr, nullptr };
     int meta_slot = 0;
     size_t meta_qoff = 0, meta_koff = 0, meta_thr = 0;   // byte offsets inside d_meta
-    int* d_flags() const { return d_meta.as<int>(); }
-    uint64_t* d_qoff() const { return reinterpret_cast<uint64_t*>(d_meta.as<char>() + meta_qoff); }
-    uint32_t* d_koff() const { return reinterpret_cast<uint32_t*>(d_meta.as<char>() + meta_koff); }
-    uint32_t* d_thr() const { return reinterpret_cast<uint32_t*>(d_meta.as<char>() + meta_thr); }
+    int* d_flags() const { return d_meta_[cur].as<int>(); }
+    uint64_t* d_qoff() const { return reinterpret_cast<uint64_t*>(d_meta_[cur].as<char>() + meta_qoff); }
+    uint32_t* d_koff() const { return reinterpret_cast<uint32_t*>(d_meta_[cur].as<char>() + meta_koff); }
+    uint32_t* d_thr() const { return reinterpret_cast<uint32_t*>(d_meta_[cur].as<char>() + meta_thr); }
     // cached launch configuration of the score kernel per mode
     struct ScoreCfg {
         bool valid = false;
@@ -216,6 +225,12 @@ struct cobsgpu_index {
         if (d_tiles) cudaFree(d_tiles);
         if (d_seg) cudaFree(d_seg);
         if (d_work) cudaFree(d_work);
+        if (pre_stream) {
+            cudaStreamSynchronize(pre_stream);
+            cudaStreamDestroy(pre_stream);
+        }
+        for (cudaEvent_t e : { ev_in, ev_k1[0], ev_k1[1], ev_k2[0], ev_k2[1] })
+            if (e) cudaEventDestroy(e);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
 };
@@ -583,7 +598,7 @@ void prepare_batch(cobsgpu_index* ix, const char* queries, bool dev_queries,
         ix->meta_koff = ix->meta_qoff + (static_cast<size_t>(nq) + 1) * 8;
         ix->meta_thr = ix->meta_koff + round_up<size_t>((static_cast<size_t>(nq) + 1) * 4, 8);
         const size_t meta_bytes = ix->meta_thr + std::max<size_t>(nq, 1) * 4;
-        ix->d_meta.ensure(meta_bytes);
+        ix->meta().ensure(meta_bytes);
         const int slot = ix->meta_slot;
         ix->meta_slot = (slot + 1) % cobsgpu_index::META_RING;
         if (!ix->meta_ev[slot]) CK(cudaEventCreateWithFlags(&ix->meta_ev[slot], cudaEventDisableTiming));
@@ -595,10 +610,10 @@ void prepare_batch(cobsgpu_index* ix, const char* queries, bool dev_queries,
         std::memcpy(hm + ix->meta_qoff, ix->b_qoff.data(), (static_cast<size_t>(nq) + 1) * 8);
         std::memcpy(hm + ix->meta_koff, ix->b_koff.data(), (static_cast<size_t>(nq) + 1) * 4);
         if (nq) std::memcpy(hm + ix->meta_thr, ix->b_thr.data(), static_cast<size_t>(nq) * 4);
-        CK(cudaMemcpyAsync(ix->d_meta.p, hm, meta_bytes, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ix->meta().p, hm, meta_bytes, cudaMemcpyHostToDevice, st));
         CK(cudaEventRecord(ix->meta_ev[slot], st));
     }
-    ix->d_hashes.ensure(std::max<uint64_t>(1, kmers) * ix->num_hashes * 8);
+    ix->hashes().ensure(std::max<uint64_t>(1, kmers) * ix->num_hashes * 8);
     if (kmers) {
         HashParams hp{};
         hp.queries = ix->b_dev_queries;
@@ -610,7 +625,7 @@ void prepare_batch(cobsgpu_index* ix, const char* queries, bool dev_queries,
         hp.k = k;
         hp.h = ix->num_hashes;
         hp.canonicalize = ix->canonicalize;
-        hp.hashes = ix->d_hashes.as<uint64_t>();
+        hp.hashes = ix->hashes().as<uint64_t>();
         hp.first_bad = ix->d_flags();
         PhaseScope ps(ix, PH_HASH, st);
         const uint32_t grid = div_ceil<uint32_t>(ix->b_total_kmers, 128);
@@ -629,7 +644,7 @@ ScoreParams base_params(cobsgpu_index* ix, const uint32_t* d_qlist, uint32_t n_s
     sp.tiles = ix->d_tiles;
     sp.n_tiles = static_cast<uint32_t>(ix->tiles.size());
     sp.h = ix->num_hashes;
-    sp.hashes = ix->d_hashes.as<uint64_t>();
+    sp.hashes = ix->hashes().as<uint64_t>();
     sp.koff = ix->d_koff();
     sp.qlist = d_qlist;
     sp.nq_items = n_slots;
@@ -1038,6 +1053,8 @@ int cobsgpu_set_option(cobsgpu_index* ix, const char* name, int64_t value) {
         else if (n == "max_batch" && value >= 1) ix->max_batch = static_cast<uint32_t>(std::min<int64_t>(value, 1 << 22));
         else if (n == "workspace_mb" && value >= 1) ix->workspace_bytes = static_cast<uint64_t>(value) << 20;
         else if (n == "timing") ix->timing = value != 0;
+        else if (n == "prefetch") ix->prefetch = value != 0;
+        else if (n == "inputs_ready") ix->inputs_ready = value != 0;
         else throw Err{ COBSGPU_ERR_INVALID_ARG, "unknown option or bad value: " + n };
     });
 }
@@ -1052,7 +1069,7 @@ int cobsgpu_hash(cobsgpu_index* ix, const char* queries, const uint64_t* offsets
             const uint32_t q1 = next_batch_end(ix, offsets, q0, nq);
             prepare_batch(ix, queries, false, offsets, q0, q1, 0.0, ix->stream);
             const uint64_t n = static_cast<uint64_t>(ix->b_total_kmers) * ix->num_hashes;
-            CK(cudaMemcpyAsync(out + done, ix->d_hashes.p, n * 8, cudaMemcpyDeviceToHost, ix->stream));
+            CK(cudaMemcpyAsync(out + done, ix->hashes().p, n * 8, cudaMemcpyDeviceToHost, ix->stream));
             check_bad_base(ix, q0, ix->stream);
             done += n;
             q0 = q1;
@@ -1147,7 +1164,42 @@ int cobsgpu_search_batch_device(cobsgpu_index* ix, const char* d_queries, const 
         if (nq == 0) return;
         CK(cudaSetDevice(ix->device));
         cudaStream_t st = static_cast<cudaStream_t>(stream);
-        prepare_batch(ix, d_queries, true, offsets, 0, nq, threshold, st);
+        // "prefetch": metadata upload + K1 run ahead on an internal stream, on the buffer set
+        // the previous call does not use, and only K2/K3 are ordered on the caller's stream
+        int set = -1;
+        cudaStream_t ks = st;
+        if (ix->prefetch) {
+            if (!ix->pre_stream) {
+                CK(cudaStreamCreateWithFlags(&ix->pre_stream, cudaStreamNonBlocking));
+                CK(cudaEventCreateWithFlags(&ix->ev_in, cudaEventDisableTiming));
+                for (int i = 0; i < 2; ++i) {
+                    CK(cudaEventCreateWithFlags(&ix->ev_k1[i], cudaEventDisableTiming));
+                    CK(cudaEventCreateWithFlags(&ix->ev_k2[i], cudaEventDisableTiming));
+                }
+            }
+            ix->cur ^= 1;
+            set = ix->cur;
+            ks = ix->pre_stream;
+            if (!ix->inputs_ready) {   // d_queries may still be produced on the caller's stream
+                CK(cudaEventRecord(ix->ev_in, st));
+                CK(cudaStreamWaitEvent(ks, ix->ev_in, 0));
+            }
+            if (ix->ev_k2_valid[set]) CK(cudaStreamWaitEvent(ks, ix->ev_k2[set], 0));
+        }
+        prepare_batch(ix, d_queries, true, offsets, 0, nq, threshold, ks);
+        if (set >= 0) {
+            CK(cudaEventRecord(ix->ev_k1[set], ks));
+            CK(cudaStreamWaitEvent(st, ix->ev_k1[set], 0));
+        }
+        struct K2Done {   // marks the buffer set free once K2/K3 of this call are enqueued
+            cobsgpu_index* ix;
+            int set;
+            cudaStream_t st;
+            ~K2Done() {
+                if (set >= 0 && cudaEventRecord(ix->ev_k2[set], st) == cudaSuccess)
+                    ix->ev_k2_valid[set] = true;
+            }
+        } k2done{ ix, set, st };
         for (uint32_t i = 0; i < nq; ++i)
             if (ix->b_koff[i + 1] - ix->b_koff[i] > 255)
                 throw Err{ COBSGPU_ERR_INVALID_ARG,

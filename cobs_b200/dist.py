@@ -22,13 +22,20 @@ class ShardedSearch:
     All ranks must call search_device() with the same queries; every rank ends up with the
     same merged result."""
 
-    def __init__(self, index, rank=0, world=1, results_per_query=64, group=None):
+    def __init__(self, index, rank=0, world=1, results_per_query=64, group=None, overlap=False):
+        """overlap=True (world > 1): the all-gather + merge of a call run on a side stream and
+        alternate between two buffer sets, so they overlap the next call's score kernel.  The
+        returned tensors are then only valid after join() / synchronize()."""
         self.index = index
         self.rank = rank
         self.world = world
         self.rpq = results_per_query
         self.group = group
+        self.overlap = bool(overlap) and world > 1
         self._bufs = {}
+        self._parity = 0
+        self._comm_stream = None
+        self._comm_done = [None, None]
 
     # -- hooks (overridden by the CPU/gloo protocol test) -------------------------------
     def _local_search(self, d_queries, off, threshold, num_results, counts, keys):
@@ -50,11 +57,11 @@ class ShardedSearch:
         cap = self.rpq * self.world
         return cap if num_results == 0 else min(num_results, cap)
 
-    def _buffers(self, nq, k, dev):
+    def _buffers(self, nq, k, dev, parity=0):
         """Per (nq, k) work buffers, allocated once.  A rank's result block is ONE int64
         tensor [counts (nq x int32, padded) | keys (nq x rpq)], so a single all-gather moves
         everything."""
-        key = (nq, k, str(dev))
+        key = (nq, k, str(dev), parity)
         b = self._bufs.get(key)
         if b is None:
             h = (nq + 1) // 2                      # int64 words holding the int32 counts
@@ -78,19 +85,47 @@ class ShardedSearch:
     def search_device(self, d_queries, off, threshold, num_results):
         """d_queries: uint8 tensor on this rank's device holding the packed batch; off: host
         uint64[nq+1].  Returns (counts int32[nq], keys int64[nq, out_per_query]) on the device
-        (buffers owned by this object, overwritten by the next call with the same shape);
+        (buffers owned by this object, overwritten by a later call with the same shape);
         key = (~score << 32) | global_doc, ascending == (score desc, doc asc); a count of
         0xFFFFFFFF (as uint32) flags a query whose candidates overflowed on some rank."""
         nq = len(off) - 1
         k = self.out_per_query(num_results)
-        b = self._buffers(nq, k, d_queries.device)
+        if not self.overlap:
+            b = self._buffers(nq, k, d_queries.device)
+            self._local_search(d_queries, off, threshold, num_results, b["counts"], b["keys"])
+            if self.world == 1:
+                return b["counts"], b["keys"][:, :k]
+            # rank-major concatenation along dim 0 (the layout both NCCL and gloo accept)
+            dist.all_gather_into_tensor(b["gathered"], b["block"], group=self.group)
+            self._merge(b["all_counts"], b["all_keys"], num_results, b["out_counts"],
+                        b["out_keys"])
+            return b["out_counts"], b["out_keys"]
+        # pipelined: local search on the current stream, exchange + merge on a side stream
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=d_queries.device, priority=-1)
+        self._parity ^= 1
+        par = self._parity
+        b = self._buffers(nq, k, d_queries.device, par)
+        main = torch.cuda.current_stream()
+        if self._comm_done[par] is not None:
+            main.wait_event(self._comm_done[par])      # buffer set free again
         self._local_search(d_queries, off, threshold, num_results, b["counts"], b["keys"])
-        if self.world == 1:
-            return b["counts"], b["keys"][:, :k]
-        # rank-major concatenation along dim 0 (the layout both NCCL and gloo accept)
-        dist.all_gather_into_tensor(b["gathered"], b["block"], group=self.group)
-        self._merge(b["all_counts"], b["all_keys"], num_results, b["out_counts"], b["out_keys"])
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(self._comm_stream):
+            self._comm_stream.wait_event(ready)
+            dist.all_gather_into_tensor(b["gathered"], b["block"], group=self.group)
+            self._merge(b["all_counts"], b["all_keys"], num_results, b["out_counts"],
+                        b["out_keys"])
+            done = torch.cuda.Event()
+            done.record(self._comm_stream)
+        self._comm_done[par] = done
         return b["out_counts"], b["out_keys"]
+
+    def join(self):
+        """make the current stream wait for the pending exchange/merge work"""
+        if self._comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self._comm_stream)
 
     def search_host(self, h_queries, off, threshold, num_results):
         """end-to-end variant: h_queries is a (pinned) host uint8 tensor; returns numpy
@@ -98,6 +133,7 @@ class ShardedSearch:
         dev = torch.device("cuda", torch.cuda.current_device())
         d_q = h_queries.to(dev, non_blocking=True)
         counts, keys = self.search_device(d_q, off, threshold, num_results)
+        self.join()
         c = counts.cpu().numpy().view(np.uint32)
         valid = c[c != OVERFLOW]
         kmax = int(valid.max()) if valid.size else 0

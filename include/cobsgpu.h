@@ -142,7 +142,11 @@ const char* cobsgpu_index_doc_name(const cobsgpu_index* idx, uint32_t doc);
 
 /* options: "max_candidates" (per-query candidate slots of the fused threshold path,
  * default 1024), "max_batch" (queries per device batch, default 16384),
- * "workspace_mb" (bound for the exhaustive path, default 1024), "timing" (0/1) */
+ * "workspace_mb" (bound for the exhaustive path, default 1024), "timing" (0/1),
+ * "prefetch" (0/1: cobsgpu_search_batch_device runs the metadata upload + K1 of a call on an
+ * internal stream, double-buffered, so that they overlap the previous call's K2),
+ * "inputs_ready" (0/1: with prefetch, the caller guarantees d_queries is already complete --
+ * otherwise the internal stream first waits for the caller's stream) */
 int cobsgpu_set_option(cobsgpu_index* idx, const char* name, int64_t value);
 
 /*
@@ -178,7 +182,9 @@ int cobsgpu_search_batch(cobsgpu_index* idx, const char* queries,
  * (max(results_per_query, "max_candidates")) gets d_counts[q] = UINT32_MAX instead of an
  * incomplete list (nothing is silently dropped); redo it through cobsgpu_search_batch.
  * Queries are limited to 255 k-mers on this path.
- * All work is enqueued on `stream` (a cudaStream_t, may be 0) and is asynchronous.
+ * All work is enqueued on `stream` (a cudaStream_t, may be 0) and is asynchronous; calls on
+ * one handle must be issued from one thread, and the stream must be synchronised before the
+ * host-buffer entry points are used on the same handle.
  */
 int cobsgpu_search_batch_device(cobsgpu_index* idx, const char* d_queries,
                                 const uint64_t* offsets, uint32_t nq,

@@ -346,3 +346,41 @@ def test_timers_and_launch_counts():
     assert t["score_launches"] == 1 and t["kernel_launches"] >= 4
     assert t["score_ms"] > 0 and t["hashes_ms"] > 0
     g.close()
+
+
+def test_device_path_prefetch_pipeline():
+    """"prefetch": K1 of call i+1 runs on an internal stream while K2 of call i is in flight
+    (double-buffered metadata / hashes).  Many back-to-back calls with different batches and
+    per-call output buffers must give exactly what the host path gives."""
+    torch = pytest.importorskip("torch")
+    g, o = pair(KIND_CLASSIC, 4000, [23], 3, seed=31)
+    nq, rpq, n_calls = 300, 32, 9
+    batches = [[rq(1000 * c + i, 100) for i in range(nq)] for c in range(n_calls)]
+    want = [g.search_batch(b, 0.3, 0) for b in batches]
+    off = np.arange(nq + 1, dtype=np.uint64) * 100
+    d_q = [torch.frombuffer(bytearray(b"".join(b)), dtype=torch.uint8).cuda() for b in batches]
+    counts = torch.zeros((n_calls, nq), dtype=torch.int32, device="cuda")
+    keys = torch.zeros((n_calls, nq, rpq), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    g.set_option("prefetch", 1)
+    for ready in (1, 0):
+        g.set_option("inputs_ready", ready)
+        counts.zero_()
+        keys.zero_()
+        torch.cuda.synchronize()
+        st = torch.cuda.current_stream().cuda_stream
+        for c in range(n_calls):
+            g.search_device(d_q[c].data_ptr(), off, 0.3, 0, rpq, counts[c].data_ptr(),
+                            keys[c].data_ptr(), st)
+        torch.cuda.synchronize()
+        cc = counts.cpu().numpy()
+        kk = keys.cpu().numpy().view(np.uint64)
+        for c in range(n_calls):
+            for i in range(nq):
+                doc, score = cobs_b200.decode_keys(kk[c, i, :cc[c, i]])
+                assert np.array_equal(doc, want[c][i][0]) and np.array_equal(score, want[c][i][1])
+    # and the host path still works on the same handle afterwards
+    g.set_option("prefetch", 0)
+    for q, r in zip(batches[0][:5], g.search_batch(batches[0][:5], 0.3, 0)):
+        assert as_list(r) == oracle.search(o, q, 0.3, 0)
+    g.close()
