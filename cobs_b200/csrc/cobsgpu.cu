@@ -16,7 +16,9 @@
 #include <climits>
 #include <cmath>
 #include <cstdio>
+#include <cerrno>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <string>
 #include <vector>
@@ -414,8 +416,36 @@ void build_tiles(cobsgpu_index* ix) {
     }
 }
 
+// Fills dst with source rows [row0, row0 + nrows) of GLOBAL page `page`, full source rows of
+// page_size_src bytes each (memcpy from host pointers, or pread from the index file).
+using RowReader = std::function<void(uint32_t page, uint64_t row0, uint64_t nrows, uint8_t* dst)>;
+
+// Streams one page into HBM: the host thread reads chunk i+1 into one pinned staging buffer
+// while the DMA engine re-pitches chunk i out of the other (source row stride page_size ->
+// device pitch, only this shard's column bytes).  The analogue of the reference's
+// --load-complete read loop (cobs/util/query.cpp:56-86), with HBM as the destination.
+void stream_page(cobsgpu_index* ix, const LocalPage& lp, const RowReader& read, PinBuf (&stage)[2],
+                 cudaEvent_t (&ev)[2], int& slot) {
+    const uint64_t ps = ix->page_size_src;
+    const uint64_t target = 64ull << 20;
+    const uint64_t chunk_rows = std::max<uint64_t>(1, target / std::max<uint64_t>(1, ps));
+    CK(cudaMemsetAsync(lp.d_base, 0, lp.sig * lp.pitch, ix->stream));   // zero padding
+    for (uint64_t r = 0; r < lp.sig; r += chunk_rows) {
+        const uint64_t nr = std::min<uint64_t>(chunk_rows, lp.sig - r);
+        stage[slot].ensure(nr * ps);
+        if (!ev[slot]) CK(cudaEventCreateWithFlags(&ev[slot], cudaEventDisableTiming));
+        else CK(cudaEventSynchronize(ev[slot]));   // DMA out of this buffer has finished
+        uint8_t* buf = stage[slot].as<uint8_t>();
+        read(lp.global_page, r, nr, buf);
+        CK(cudaMemcpy2DAsync(lp.d_base + r * lp.pitch, lp.pitch, buf + lp.byte_begin, ps,
+                             lp.row_bytes, nr, cudaMemcpyHostToDevice, ix->stream));
+        CK(cudaEventRecord(ev[slot], ix->stream));
+        slot ^= 1;
+    }
+}
+
 void open_common(cobsgpu_index* ix, const std::vector<uint64_t>& sig,
-                 const uint8_t* const* page_data, uint64_t fill_seed) {
+                 const RowReader* reader, uint64_t fill_seed) {
     check_device(ix->device);
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, ix->device));
@@ -445,18 +475,19 @@ void open_common(cobsgpu_index* ix, const std::vector<uint64_t>& sig,
             lp.d_base = ix->d_arena + off;
             off += round_up<uint64_t>(lp.sig * lp.pitch, 256);
         }
+        PinBuf stage[2];
+        cudaEvent_t ev[2] = { nullptr, nullptr };
+        int slot = 0;
+        struct EvGuard {
+            cudaEvent_t (&ev)[2];
+            ~EvGuard() {
+                for (cudaEvent_t e : ev)
+                    if (e) cudaEventDestroy(e);
+            }
+        } guard{ ev };
         for (auto& lp : ix->pages) {
-            if (page_data) {
-                // re-pitch while copying: source row stride page_size -> device pitch
-                CK(cudaMemsetAsync(lp.d_base, 0, lp.sig * lp.pitch, ix->stream));
-                const uint8_t* src = page_data[lp.global_page] + lp.byte_begin;
-                const uint64_t chunk = std::max<uint64_t>(1, (256ull << 20) / std::max<uint64_t>(1, ix->page_size_src));
-                for (uint64_t r = 0; r < lp.sig; r += chunk) {
-                    const uint64_t nr = std::min<uint64_t>(chunk, lp.sig - r);
-                    CK(cudaMemcpy2DAsync(lp.d_base + r * lp.pitch, lp.pitch,
-                                         src + r * ix->page_size_src, ix->page_size_src,
-                                         lp.row_bytes, nr, cudaMemcpyHostToDevice, ix->stream));
-                }
+            if (reader) {
+                stream_page(ix, lp, *reader, stage, ev, slot);
             } else {
                 FillParams fp{ lp.d_base, lp.sig, lp.pitch, lp.row_bytes, lp.byte_begin, fill_seed,
                                lp.global_page };
@@ -976,7 +1007,16 @@ int cobsgpu_index_open(const cobsgpu_index_desc* d, cobsgpu_index** out) {
         if (ix->page_size_src * 8 * d->n_pages > 0xFFFFFFFFull)
             throw Err{ COBSGPU_ERR_INVALID_ARG, "more than 2^32 document columns" };
         std::vector<uint64_t> sig(d->signature_sizes, d->signature_sizes + d->n_pages);
-        open_common(ix.get(), sig, d->page_data, d->fill_seed);
+        if (d->page_data) {
+            const uint8_t* const* pd = d->page_data;
+            const uint64_t ps = ix->page_size_src;
+            RowReader rd = [pd, ps](uint32_t page, uint64_t row0, uint64_t nrows, uint8_t* dst) {
+                std::memcpy(dst, pd[page] + row0 * ps, nrows * ps);
+            };
+            open_common(ix.get(), sig, &rd, 0);
+        } else {
+            open_common(ix.get(), sig, nullptr, d->fill_seed);
+        }
         *out = ix.release();
     });
 }
@@ -1005,7 +1045,21 @@ int cobsgpu_index_open_file(const char* path, int device, uint32_t shard_index,
         ix->doc_names = f->doc_names;
         if (ix->page_size_src * 8 * ix->n_pages_global > 0xFFFFFFFFull)
             throw Err{ COBSGPU_ERR_INVALID_ARG, "more than 2^32 document columns" };
-        open_common(ix.get(), f->signature_sizes, f->page_data.data(), 0);
+        // matrix bytes are pread() straight into the pinned staging buffers
+        IndexFile* fp = f.get();
+        const uint64_t ps = ix->page_size_src;
+        RowReader rd = [fp, ps](uint32_t page, uint64_t row0, uint64_t nrows, uint8_t* dst) {
+            uint64_t pos = static_cast<uint64_t>(fp->page_data[page] - fp->map) + row0 * ps;
+            uint64_t left = nrows * ps;
+            while (left) {
+                ssize_t n = pread(fp->fd, dst, left, static_cast<off_t>(pos));
+                if (n <= 0) throw Err{ COBSGPU_ERR_IO, std::string("read failed: ") + std::strerror(errno) };
+                dst += n;
+                pos += static_cast<uint64_t>(n);
+                left -= static_cast<uint64_t>(n);
+            }
+        };
+        open_common(ix.get(), f->signature_sizes, &rd, 0);
         f->close();   // the matrix now lives in HBM
         *out = ix.release();
     });

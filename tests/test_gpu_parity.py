@@ -384,3 +384,39 @@ def test_device_path_prefetch_pipeline():
     for q, r in zip(batches[0][:5], g.search_batch(batches[0][:5], 0.3, 0)):
         assert as_list(r) == oracle.search(o, q, 0.3, 0)
     g.close()
+
+
+def test_loader_streams_large_file_in_chunks(tmp_path):
+    """index files are pread() through two pinned staging buffers (64 MB chunks) and re-pitched
+    by the DMA engine: a file spanning several chunks, unaligned rows, three pages, and a
+    document-axis shard of it all read back bit-exactly"""
+    n_docs, ps, sig = 9000, 1125, [70_001, 50_000, 33_333]     # 172 MB of matrix
+    o = oracle.Index.procedural(KIND_COMPACT, n_docs, sig, 2, page_size=ps, fill_seed=77)
+    path = str(tmp_path / "big.cobs_compact")
+    o.write(path)
+    g = GpuIndex.open_file(path)
+    assert g.n_docs == n_docs and g.num_hashes == 2
+    for p, s_ in enumerate(sig):
+        for r in (0, 1, 59_651, 59_652, s_ // 2, s_ - 1):    # 59 652 = rows per 64 MB chunk
+            if r >= s_:
+                continue
+            want = np.array([oracle.fill_word(77, p, r, w) for w in range((ps + 7) // 8)],
+                            dtype="<u8").view(np.uint8)[:ps]
+            assert np.array_equal(g.read_row(p, r, 0, ps), want)
+    queries = [rq(i, 120) for i in range(3)]
+    for q, a in zip(queries, g.scores(queries)):
+        assert np.array_equal(a, o.scores(q))
+    g.close()
+    # classic file, second of three column shards
+    n_docs, sig = 70_000, [9_001]                              # 78.8 MB
+    o = oracle.Index.procedural(KIND_CLASSIC, n_docs, sig, 3, fill_seed=78)
+    path = str(tmp_path / "big.cobs_classic")
+    o.write(path)
+    g = GpuIndex.open_file(path, shard_index=1, shard_count=3)
+    b0 = g.info.shard_doc_begin // 8
+    nb = (g.info.shard_doc_end - g.info.shard_doc_begin) // 8
+    for r in (0, 7_668, 7_669, 9_000):
+        row = np.array([oracle.fill_word(78, 0, r, w) for w in range(8750 // 8 + 1)],
+                       dtype="<u8").view(np.uint8)[:8750]
+        assert np.array_equal(g.read_row(0, r, 0, nb), row[b0:b0 + nb])
+    g.close()
