@@ -181,11 +181,12 @@ struct cobsgpu_index {
     PinBuf h_meta[META_RING];
     cudaEvent_t meta_ev[META_RING] = { nullptr, nullptr, nullptr, nullptr };
     int meta_slot = 0;
-    size_t meta_qoff = 0, meta_koff = 0, meta_thr = 0;   // byte offsets inside d_meta
+    size_t meta_qoff = 0, meta_koff = 0, meta_thr = 0, meta_bad = 0;   // byte offsets inside d_meta
     int* d_flags() const { return d_meta_[cur].as<int>(); }
     uint64_t* d_qoff() const { return reinterpret_cast<uint64_t*>(d_meta_[cur].as<char>() + meta_qoff); }
     uint32_t* d_koff() const { return reinterpret_cast<uint32_t*>(d_meta_[cur].as<char>() + meta_koff); }
     uint32_t* d_thr() const { return reinterpret_cast<uint32_t*>(d_meta_[cur].as<char>() + meta_thr); }
+    uint32_t* d_bad() const { return reinterpret_cast<uint32_t*>(d_meta_[cur].as<char>() + meta_bad); }
     // cached launch configuration of the score kernel per mode
     struct ScoreCfg {
         bool valid = false;
@@ -624,11 +625,12 @@ void prepare_batch(cobsgpu_index* ix, const char* queries, bool dev_queries,
             CK(cudaMemcpyAsync(ix->d_queries.p, queries + base, blob_bytes, cudaMemcpyHostToDevice, st));
             ix->b_dev_queries = ix->d_queries.as<char>();
         }
-        // one block, one copy: flags | qoff | koff | thr
+        // one block, one copy: flags | qoff | koff | thr | bad
         ix->meta_qoff = 8;
         ix->meta_koff = ix->meta_qoff + (static_cast<size_t>(nq) + 1) * 8;
         ix->meta_thr = ix->meta_koff + round_up<size_t>((static_cast<size_t>(nq) + 1) * 4, 8);
-        const size_t meta_bytes = ix->meta_thr + std::max<size_t>(nq, 1) * 4;
+        ix->meta_bad = ix->meta_thr + std::max<size_t>(nq, 1) * 4;
+        const size_t meta_bytes = ix->meta_bad + std::max<size_t>(nq, 1) * 4;
         ix->meta().ensure(meta_bytes);
         const int slot = ix->meta_slot;
         ix->meta_slot = (slot + 1) % cobsgpu_index::META_RING;
@@ -641,6 +643,7 @@ void prepare_batch(cobsgpu_index* ix, const char* queries, bool dev_queries,
         std::memcpy(hm + ix->meta_qoff, ix->b_qoff.data(), (static_cast<size_t>(nq) + 1) * 8);
         std::memcpy(hm + ix->meta_koff, ix->b_koff.data(), (static_cast<size_t>(nq) + 1) * 4);
         if (nq) std::memcpy(hm + ix->meta_thr, ix->b_thr.data(), static_cast<size_t>(nq) * 4);
+        std::memset(hm + ix->meta_bad, 0, std::max<size_t>(nq, 1) * 4);
         CK(cudaMemcpyAsync(ix->meta().p, hm, meta_bytes, cudaMemcpyHostToDevice, st));
         CK(cudaEventRecord(ix->meta_ev[slot], st));
     }
@@ -658,6 +661,7 @@ void prepare_batch(cobsgpu_index* ix, const char* queries, bool dev_queries,
         hp.canonicalize = ix->canonicalize;
         hp.hashes = ix->hashes().as<uint64_t>();
         hp.first_bad = ix->d_flags();
+        hp.bad = ix->d_bad();
         PhaseScope ps(ix, PH_HASH, st);
         const uint32_t grid = div_ceil<uint32_t>(ix->b_total_kmers, 128);
         // k = 31 is what COBS indices use in practice: k-mer bytes held in registers
@@ -1270,8 +1274,8 @@ int cobsgpu_search_batch_device(cobsgpu_index* ix, const char* d_queries, const 
             sp.cap = cap;
             launch_score(ix, sp, MODE_CAND, st);
             PhaseScope ps(ix, PH_SELECT, st);
-            FinalizeParams fp{ sp.cand, sp.cand_count, cap, nq, num_results, d_keys, d_counts,
-                               results_per_query };
+            FinalizeParams fp{ sp.cand, sp.cand_count, ix->d_bad(), cap, nq, num_results, d_keys,
+                               d_counts, results_per_query };
             finalize_strided_kernel<<<div_ceil<uint32_t>(nq, FIN_WARPS), FIN_WARPS * 32, 0, st>>>(fp);
             CK(cudaGetLastError());
             ix->tm.kernel_launches++;
@@ -1289,6 +1293,7 @@ int cobsgpu_search_batch_device(cobsgpu_index* ix, const char* d_queries, const 
         gp.large_in_scratch = lis ? 1 : 0;
         gp.out_keys = d_keys;
         gp.out_counts = d_counts;
+        gp.bad = ix->d_bad();
         gp.stride = results_per_query;
         gather_kernel<<<nq, 256, 0, st>>>(gp);
         CK(cudaGetLastError());

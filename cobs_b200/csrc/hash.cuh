@@ -23,6 +23,7 @@ struct HashParams {
     uint32_t canonicalize;
     uint64_t* hashes;         // device [total_kmers * h]
     int* first_bad;           // device: min query index holding a non-ACGT base (canonical only)
+    uint32_t* bad;            // device [nq], zero-initialised: set to 1 for such queries
 };
 
 namespace xxh {
@@ -269,7 +270,10 @@ __global__ void __launch_bounds__(128) hash_kmers_kernel(HashParams p) {
         good = hash_kmer<0>(s, p.k, p.h, p.canonicalize,
                             [&](uint32_t j, uint64_t v) { out[j] = v; });
     }
-    if (!good) atomicMin(p.first_bad, static_cast<int>(q));
+    if (!good) {
+        atomicMin(p.first_bad, static_cast<int>(q));
+        p.bad[q] = 1;
+    }
 }
 
 }  // namespace cobsgpu

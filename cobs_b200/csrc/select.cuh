@@ -15,6 +15,9 @@ static constexpr uint32_t SORT_SMALL_MAX = 2048;   // keys sorted in shared memo
 static constexpr uint32_t SORT_SMALL_THREADS = 256;
 static constexpr uint32_t SORT_LARGE_THREADS = 1024;
 static constexpr uint32_t MERGE_MAX = 8192;        // keys per query in the shard merge
+// per-query result counts of the device-resident path that flag a query instead of a list
+static constexpr uint32_t COUNT_OVERFLOW = 0xFFFFFFFFu;   // more candidates than slots
+static constexpr uint32_t COUNT_INVALID = 0xFFFFFFFEu;    // non-ACGT base, canonicalising index
 
 // in-place ascending bitonic sort of n_pow2 keys in shared memory by the whole CTA
 __device__ __forceinline__ void block_bitonic_sort(uint64_t* s, uint32_t n_pow2) {
@@ -271,6 +274,7 @@ struct GatherParams {
     // strided
     uint64_t* out_keys;
     uint32_t* out_counts;
+    const uint32_t* bad;       // [nq] by batch query, strided mode only
     uint32_t stride;
 };
 
@@ -287,7 +291,9 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherParams p) {
         for (uint32_t i = threadIdx.x; i < r && i < p.stride; i += blockDim.x) o[i] = keys[i];
         // more candidates than slots: the list would be incomplete -> flagged, never silent
         if (threadIdx.x == 0)
-            p.out_counts[q] = p.cand_count[qi] > p.cap ? 0xFFFFFFFFu : (r < p.stride ? r : p.stride);
+            p.out_counts[q] = (p.bad && p.bad[q]) ? COUNT_INVALID
+                              : p.cand_count[qi] > p.cap ? COUNT_OVERFLOW
+                                                         : (r < p.stride ? r : p.stride);
     } else {
         const uint64_t off = p.offsets[q];
         for (uint32_t i = threadIdx.x; i < r; i += blockDim.x) {
@@ -307,11 +313,12 @@ static constexpr uint32_t FIN_WARPS = 8;
 struct FinalizeParams {
     const uint64_t* cand;
     const uint32_t* cand_count;
+    const uint32_t* bad;    // [nq] != 0: query holds a non-ACGT base (canonicalising index)
     uint32_t cap;
     uint32_t nq;
     uint64_t limit;
     uint64_t* out_keys;     // [nq * stride]
-    uint32_t* out_counts;   // [nq]; 0xFFFFFFFF when the candidates overflowed `cap`
+    uint32_t* out_counts;   // [nq]; COUNT_OVERFLOW / COUNT_INVALID flag incomplete queries
     uint32_t stride;
 };
 
@@ -327,8 +334,9 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_strided_kernel(Finali
         n = c < p.cap ? c : p.cap;
         r = (p.limit != 0 && n > p.limit) ? static_cast<uint32_t>(p.limit) : n;
         if (r > p.stride) r = p.stride;
-        if (lane == 0) p.out_counts[q] = c > p.cap ? 0xFFFFFFFFu : r;
-        if (c > p.cap) n = 0;   // flagged: the list would be incomplete
+        const bool invalid = p.bad[q] != 0;
+        if (lane == 0) p.out_counts[q] = invalid ? COUNT_INVALID : (c > p.cap ? COUNT_OVERFLOW : r);
+        if (c > p.cap || invalid) n = 0;   // flagged: the list would be incomplete / meaningless
         if (n > 32) {
             if (lane == 0) big_n[warp] = n;
         } else if (n > 0) {
@@ -383,7 +391,7 @@ __global__ void __launch_bounds__(256) merge_kernel(MergeParams p) {
         uint32_t t = 0, o = 0;
         for (uint32_t l = 0; l < p.n_lists; ++l) {
             const uint32_t c = p.counts[l * p.counts_list_stride + q];
-            if (c == 0xFFFFFFFFu) o = 1;   // a shard overflowed its candidate slots
+            if (c >= COUNT_INVALID) o = o > c ? o : c;   // a shard flagged the query
             else t += c < p.stride ? c : p.stride;
         }
         tot = t;
@@ -391,7 +399,7 @@ __global__ void __launch_bounds__(256) merge_kernel(MergeParams p) {
     }
     __syncthreads();
     if (ovf) {
-        if (threadIdx.x == 0) p.out_counts[q] = 0xFFFFFFFFu;
+        if (threadIdx.x == 0) p.out_counts[q] = ovf;
         return;
     }
     const uint32_t total = tot;
@@ -399,7 +407,7 @@ __global__ void __launch_bounds__(256) merge_kernel(MergeParams p) {
     uint32_t start = 0;
     for (uint32_t l = 0; l < p.n_lists; ++l) {
         uint32_t c = p.counts[l * p.counts_list_stride + q];
-        if (c > p.stride) c = p.stride;
+        if (c > p.stride) c = p.stride;   // (flagged lists returned above)
         const uint64_t* src = p.keys + l * p.keys_list_stride + static_cast<uint64_t>(q) * p.stride;
         for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) ms[start + i] = src[i];
         start += c;

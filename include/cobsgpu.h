@@ -40,6 +40,10 @@ extern "C" {
 #define COBSGPU_ERR_BAD_FILE 6
 #define COBSGPU_ERR_IO 7
 
+/* per-query counts of the device-resident path that flag a query instead of a list */
+#define COBSGPU_COUNT_OVERFLOW 0xFFFFFFFFu
+#define COBSGPU_COUNT_INVALID 0xFFFFFFFEu
+
 #define COBSGPU_KIND_CLASSIC 0
 #define COBSGPU_KIND_COMPACT 1
 
@@ -179,8 +183,10 @@ int cobsgpu_search_batch(cobsgpu_index* idx, const char* queries,
  *   d_counts[nq]            number of results of query q (<= results_per_query)
  *   d_keys[nq * results_per_query]   sorted keys; key = (~score << 32) | doc, ascending
  * A query whose candidates overflowed the per-query candidate slots
- * (max(results_per_query, "max_candidates")) gets d_counts[q] = UINT32_MAX instead of an
- * incomplete list (nothing is silently dropped); redo it through cobsgpu_search_batch.
+ * (max(results_per_query, "max_candidates")) gets d_counts[q] = COBSGPU_COUNT_OVERFLOW
+ * instead of an incomplete list (nothing is silently dropped; redo it through
+ * cobsgpu_search_batch); a query with a non-ACGT base in a canonicalising index gets
+ * COBSGPU_COUNT_INVALID (the host entry points report COBSGPU_ERR_INVALID_BASE for it).
  * Queries are limited to 255 k-mers on this path.
  * All work is enqueued on `stream` (a cudaStream_t, may be 0) and is asynchronous; calls on
  * one handle must be issued from one thread, and the stream must be synchronised before the
@@ -197,8 +203,8 @@ int cobsgpu_search_batch_device(cobsgpu_index* idx, const char* d_queries,
  * per query of at most min(num_results or all, out_per_query) entries.  List l has its counts
  * [nq] at d_counts + l * counts_list_stride (uint32 elements) and its keys
  * [nq][results_per_query] at d_keys + l * keys_list_stride (uint64 elements); a stride of 0
- * means densely packed ([n_lists][nq] / [n_lists][nq][results_per_query]).  A count of
- * UINT32_MAX in any list propagates to the output.  Device pointers; asynchronous on `stream`. */
+ * means densely packed ([n_lists][nq] / [n_lists][nq][results_per_query]).  A flagged count
+ * (COBSGPU_COUNT_*) in any list propagates to the output.  Device pointers; asynchronous on `stream`. */
 int cobsgpu_merge_device(int device, uint32_t n_lists, uint32_t nq,
                          uint32_t results_per_query, const uint32_t* d_counts,
                          uint64_t counts_list_stride, const uint64_t* d_keys,

@@ -420,3 +420,29 @@ def test_loader_streams_large_file_in_chunks(tmp_path):
                        dtype="<u8").view(np.uint8)[:8750]
         assert np.array_equal(g.read_row(0, r, 0, nb), row[b0:b0 + nb])
     g.close()
+
+
+def test_device_path_flags_invalid_bases():
+    """non-ACGT in a canonicalising index: the host path fails the call like the reference's
+    die(); the asynchronous device path flags exactly those queries"""
+    torch = pytest.importorskip("torch")
+    g, o = pair(KIND_CLASSIC, 500, [17], 3, seed=2)
+    queries = [rq(i, 100) for i in range(6)]
+    queries[2] = queries[2][:40] + b"N" + queries[2][41:]
+    queries[5] = b"X" + queries[5][1:]
+    d_q = torch.frombuffer(bytearray(b"".join(queries)), dtype=torch.uint8).cuda()
+    off = np.arange(len(queries) + 1, dtype=np.uint64) * 100
+    counts = torch.zeros(len(queries), dtype=torch.int32, device="cuda")
+    keys = torch.zeros((len(queries), 16), dtype=torch.int64, device="cuda")
+    g.search_device(d_q.data_ptr(), off, 0.3, 0, 16, counts.data_ptr(), keys.data_ptr(),
+                    torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    c = counts.cpu().numpy().view(np.uint32)
+    kk = keys.cpu().numpy().view(np.uint64)
+    for i, q in enumerate(queries):
+        if i in (2, 5):
+            assert c[i] == 0xFFFFFFFE
+        else:
+            doc, score = cobs_b200.decode_keys(kk[i, :c[i]])
+            assert [(0, int(d), int(s)) for d, s in zip(doc, score)] == oracle.search(o, q, 0.3, 0)
+    g.close()
