@@ -13,6 +13,7 @@ synthetic queries against a synthetic index resident in HBM.  Workloads (BASELIN
         10 000 random 100-bp queries per step, threshold 0.8 (the CLI default)
   cfg4  classic, 1 000 000 docs, 1 048 573 rows (131 GB), h=3, 2 048 queries per step
   cfg3  compact, 1 000 000 docs, 8 pages of 16 384 B, h=4, 512 queries per step
+  cfg5  compact, 10 000 000 docs, 77 pages of 16 384 B (~600 GB): multi-GPU only
 For N > 1 the SAME index is sharded along the document axis (strong scaling).
 
 Every step uses a different query batch, and the row set a batch touches (>= 26 GB) is far
@@ -48,6 +49,11 @@ WORKLOADS = {
                  sig=[int(196_613 * 1.5 ** p) for p in range(8)],
                  desc="compact index, 1000000 docs, 8 pages x 16384 B, h=4, k=31, "
                       "512 random 100-bp queries/step, threshold 0.8"),
+    # BASELINE.json configs[4]: index larger than one GPU's HBM -> needs >= 4 GPUs
+    "cfg5": dict(kind=1, n_docs=10_000_000, page_size=16_384, h=4, nq=256,
+                 sig=[int(100_003 * 1.0345 ** p) for p in range(77)],
+                 desc="compact index, 10000000 docs, 77 pages x 16384 B (~600 GB, document-sharded), "
+                      "h=4, k=31, 256 random 100-bp queries/step, threshold 0.8"),
     # small variant for functional checks on any GPU
     "tiny": dict(kind=0, n_docs=100_000, sig=[65_521], page_size=0, h=3, nq=2_000,
                  desc="classic index, 100000 docs, 65521 rows (0.8 GB), h=3, k=31"),
