@@ -51,6 +51,25 @@ class IndexDesc(C.Structure):
     ]
 
 
+class ConstructDesc(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("term_size", C.c_uint32),
+        ("canonicalize", C.c_uint32),
+        ("num_hashes", C.c_uint32),
+        ("signature_size", C.c_uint64),
+        ("false_positive_rate", C.c_double),
+        ("n_docs", C.c_uint32),
+        ("n_seqs", C.c_uint32),
+        ("doc_names", C.POINTER(C.c_char_p)),
+        ("sequences", C.c_char_p),
+        ("seq_offsets", C.POINTER(C.c_uint64)),
+        ("seq_doc", C.POINTER(C.c_uint32)),
+        ("device", C.c_int32),
+        ("reserved", C.c_uint32),
+    ]
+
+
 class IndexInfo(C.Structure):
     _fields_ = [
         ("kind", C.c_int32),
@@ -101,6 +120,8 @@ SYMBOLS = {
     "cobsgpu_index_open": (C.c_int, [C.POINTER(IndexDesc), C.POINTER(C.c_void_p)]),
     "cobsgpu_index_open_file": (C.c_int, [C.c_char_p, C.c_int, C.c_uint32, C.c_uint32,
                                           C.POINTER(C.c_void_p)]),
+    "cobsgpu_construct_classic": (C.c_int, [C.POINTER(ConstructDesc), C.POINTER(C.c_void_p)]),
+    "cobsgpu_index_save": (C.c_int, [C.c_void_p, C.c_char_p]),
     "cobsgpu_index_close": (None, [C.c_void_p]),
     "cobsgpu_index_get_info": (C.c_int, [C.c_void_p, C.POINTER(IndexInfo)]),
     "cobsgpu_index_signature_size": (C.c_uint64, [C.c_void_p, C.c_uint32]),

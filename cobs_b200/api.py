@@ -94,6 +94,45 @@ class GpuIndex:
         _lib.check(_lib.lib().cobsgpu_index_open(C.byref(d), C.byref(h)))
         return cls(h.value)
 
+    @classmethod
+    def construct_classic(cls, documents, num_hashes=1, false_positive_rate=0.3, term_size=31,
+                          canonicalize=1, signature_size=0, device=0):
+        """documents: list of (name, [sequence, ...]); builds the classic index on the device
+        (the reference's classic_construct, cobs/construction/classic_index.cpp:565-600)"""
+        names, seqs, seq_doc = [], [], []
+        for i, (name, parts) in enumerate(documents):
+            names.append(name.encode() if isinstance(name, str) else name)
+            for p in parts:
+                seqs.append(p if isinstance(p, (bytes, bytearray)) else p.encode("ascii"))
+                seq_doc.append(i)
+        blob, off = _pack_queries(seqs)
+        sd = np.asarray(seq_doc, dtype=np.uint32)
+        d = _lib.ConstructDesc()
+        d.struct_size = C.sizeof(_lib.ConstructDesc)
+        d.term_size = term_size
+        d.canonicalize = canonicalize
+        d.num_hashes = num_hashes
+        d.signature_size = signature_size
+        d.false_positive_rate = false_positive_rate
+        d.n_docs = len(names)
+        d.n_seqs = len(seqs)
+        d.doc_names = (C.c_char_p * len(names))(*names)
+        d.sequences = blob
+        d.seq_offsets = off.ctypes.data_as(C.POINTER(C.c_uint64))
+        d.seq_doc = sd.ctypes.data_as(C.POINTER(C.c_uint32))
+        d.device = device
+        h = C.c_void_p()
+        _lib.check(_lib.lib().cobsgpu_construct_classic(C.byref(d), C.byref(h)))
+        return cls(h.value)
+
+    def save(self, path):
+        """write the index in the reference's file format"""
+        p = path if isinstance(path, bytes) else str(path).encode()
+        _lib.check(_lib.lib().cobsgpu_index_save(self._h, p))
+
+    def signature_size(self, page=0):
+        return _lib.lib().cobsgpu_index_signature_size(self._h, page)
+
     def close(self):
         if self._h:
             _lib.lib().cobsgpu_index_close(self._h)

@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "construct.cuh"
 #include "fill.cuh"
 #include "hash.cuh"
 #include "index_file.hpp"
@@ -446,7 +447,7 @@ void stream_page(cobsgpu_index* ix, const LocalPage& lp, const RowReader& read, 
 }
 
 void open_common(cobsgpu_index* ix, const std::vector<uint64_t>& sig,
-                 const RowReader* reader, uint64_t fill_seed) {
+                 const RowReader* reader, uint64_t fill_seed, bool zero_fill = false) {
     check_device(ix->device);
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, ix->device));
@@ -489,6 +490,8 @@ void open_common(cobsgpu_index* ix, const std::vector<uint64_t>& sig,
         for (auto& lp : ix->pages) {
             if (reader) {
                 stream_page(ix, lp, *reader, stage, ev, slot);
+            } else if (zero_fill) {
+                CK(cudaMemsetAsync(lp.d_base, 0, lp.sig * lp.pitch, ix->stream));
             } else {
                 FillParams fp{ lp.d_base, lp.sig, lp.pitch, lp.row_bytes, lp.byte_begin, fill_seed,
                                lp.global_page };
@@ -1066,6 +1069,146 @@ int cobsgpu_index_open_file(const char* path, int device, uint32_t shard_index,
         open_common(ix.get(), f->signature_sizes, &rd, 0);
         f->close();   // the matrix now lives in HBM
         *out = ix.release();
+    });
+}
+
+int cobsgpu_construct_classic(const cobsgpu_construct_desc* d, cobsgpu_index** out) {
+    return guarded([&] {
+        if (!d || !out || d->struct_size != sizeof(cobsgpu_construct_desc))
+            throw Err{ COBSGPU_ERR_INVALID_ARG, "bad cobsgpu_construct_desc" };
+        if (d->n_docs == 0 || (d->n_seqs && (!d->sequences || !d->seq_offsets || !d->seq_doc)))
+            throw Err{ COBSGPU_ERR_INVALID_ARG, "construction needs documents and sequences" };
+        const uint32_t k = d->term_size;
+        if (k == 0 || d->num_hashes == 0) throw Err{ COBSGPU_ERR_INVALID_ARG, "term_size and num_hashes must be > 0" };
+        // windows (k-mers) per sequence and per document
+        std::vector<uint64_t> win_off(static_cast<size_t>(d->n_seqs) + 1, 0), doc_terms(d->n_docs, 0);
+        for (uint32_t s = 0; s < d->n_seqs; ++s) {
+            if (d->seq_offsets[s + 1] < d->seq_offsets[s] || d->seq_doc[s] >= d->n_docs)
+                throw Err{ COBSGPU_ERR_INVALID_ARG, "bad sequence table" };
+            const uint64_t len = d->seq_offsets[s + 1] - d->seq_offsets[s];
+            const uint64_t w = len >= k ? len - k + 1 : 0;
+            win_off[s + 1] = win_off[s] + w;
+            doc_terms[d->seq_doc[s]] += w;
+        }
+        uint64_t sig = d->signature_size;
+        if (sig == 0) {
+            // classic_construct: size the filters for the largest document
+            // (cobs/construction/classic_index.cpp:571-575, cobs/util/calc_signature_size.cpp:15-33)
+            const uint64_t max_doc = *std::max_element(doc_terms.begin(), doc_terms.end());
+            const double hh = static_cast<double>(d->num_hashes);
+            const double ratio = -hh / std::log(1 - std::pow(d->false_positive_rate, 1 / hh));
+            if (!(ratio > 0)) throw Err{ COBSGPU_ERR_INVALID_ARG, "bad false_positive_rate" };
+            sig = static_cast<uint64_t>(std::ceil(static_cast<double>(max_doc) * ratio));
+        }
+        if (sig == 0) throw Err{ COBSGPU_ERR_INVALID_ARG, "signature_size is 0 (empty documents?)" };
+
+        std::unique_ptr<cobsgpu_index> ix(new cobsgpu_index);
+        ix->kind = COBSGPU_KIND_CLASSIC;
+        ix->term_size = k;
+        ix->canonicalize = d->canonicalize;
+        ix->num_hashes = d->num_hashes;
+        ix->n_docs = d->n_docs;
+        ix->n_pages_global = 1;
+        ix->page_size_src = (static_cast<uint64_t>(d->n_docs) + 7) / 8;
+        ix->device = d->device;
+        ix->shard_index = 0;
+        ix->shard_count = 1;
+        ix->doc_names.resize(d->n_docs);
+        for (uint32_t i = 0; i < d->n_docs; ++i)
+            ix->doc_names[i] = d->doc_names && d->doc_names[i] ? d->doc_names[i] : "";
+        open_common(ix.get(), { sig }, nullptr, 0, /*zero_fill=*/true);
+
+        const uint64_t total = win_off.back();
+        if (total) {
+            const uint64_t nchar = d->seq_offsets[d->n_seqs];
+            DevBuf d_seq, d_off, d_win, d_doc;
+            d_seq.ensure(nchar + 16);
+            d_off.ensure((d->n_seqs + 1) * 8);
+            d_win.ensure((d->n_seqs + 1) * 8);
+            d_doc.ensure(d->n_seqs * 4);
+            cudaStream_t st = ix->stream;
+            CK(cudaMemcpyAsync(d_seq.p, d->sequences, nchar, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(d_off.p, d->seq_offsets, (d->n_seqs + 1) * 8, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(d_win.p, win_off.data(), (d->n_seqs + 1) * 8, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(d_doc.p, d->seq_doc, d->n_seqs * 4, cudaMemcpyHostToDevice, st));
+            const LocalPage& lp = ix->pages[0];
+            ConstructParams cp{ d_seq.as<char>(), d_off.as<uint64_t>(), d_win.as<uint64_t>(),
+                                d_doc.as<uint32_t>(), d->n_seqs, total, k, d->num_hashes,
+                                d->canonicalize, sig, lp.d_base, lp.pitch };
+            const uint32_t grid = static_cast<uint32_t>(std::min<uint64_t>(
+                div_ceil<uint64_t>(total, 128), static_cast<uint64_t>(ix->sm_count) * 32));
+            construct_classic_kernel<<<grid, 128, 0, st>>>(cp);
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(st));
+        }
+        *out = ix.release();
+    });
+}
+
+int cobsgpu_index_save(const cobsgpu_index* ix, const char* path) {
+    return guarded([&] {
+        if (!ix || !path) throw Err{ COBSGPU_ERR_INVALID_ARG, "null argument" };
+        if (ix->shard_count != 1)
+            throw Err{ COBSGPU_ERR_INVALID_ARG, "only an unsharded index can be saved" };
+        CK(cudaSetDevice(ix->device));
+        FILE* f = std::fopen(path, "wb");
+        if (!f) throw Err{ COBSGPU_ERR_IO, std::string("could not open ") + path + " for writing" };
+        struct Closer {
+            FILE* f;
+            ~Closer() { std::fclose(f); }
+        } closer{ f };
+        auto put = [&](const void* p, size_t n) {
+            if (n && std::fwrite(p, 1, n, f) != n) throw Err{ COBSGPU_ERR_IO, "write failed" };
+        };
+        const bool classic = ix->kind == COBSGPU_KIND_CLASSIC;
+        const uint32_t version = 1, n_docs = ix->n_docs;
+        const uint8_t canon = static_cast<uint8_t>(ix->canonicalize);
+        const uint64_t nh = ix->num_hashes;
+        // headers: cobs/file/classic_index_header.cpp:26-36, compact_index_header.cpp:24-42
+        put("COBS:", 5);
+        put(classic ? "CLASSIC_INDEX" : "COMPACT_INDEX", 13);
+        put(&version, 4);
+        put(&ix->term_size, 4);
+        put(&canon, 1);
+        if (classic) {
+            put(&n_docs, 4);
+            put(&ix->signature_sizes[0], 8);
+            put(&nh, 8);
+        } else {
+            const uint32_t np = ix->n_pages_global;
+            put(&np, 4);
+            put(&n_docs, 4);
+            put(&ix->page_size_src, 8);
+            for (uint32_t p = 0; p < np; ++p) {
+                put(&ix->signature_sizes[p], 8);
+                put(&nh, 8);
+            }
+        }
+        for (uint32_t i = 0; i < n_docs; ++i) {
+            const std::string& nm = i < ix->doc_names.size() ? ix->doc_names[i] : std::string();
+            put(nm.data(), nm.size());
+            put("\n", 1);
+        }
+        if (!classic) {
+            const uint64_t pos = static_cast<uint64_t>(std::ftell(f));
+            const uint64_t ps = ix->page_size_src;
+            std::vector<char> pad((ps - ((pos + 13) % ps)) % ps, 0);
+            put(pad.data(), pad.size());
+        }
+        put(classic ? "CLASSIC_INDEX" : "COMPACT_INDEX", 13);
+        // matrix: device pitch -> the file's unpadded rows
+        const uint64_t ps = ix->page_size_src;
+        const uint64_t chunk_rows = std::max<uint64_t>(1, (64ull << 20) / std::max<uint64_t>(1, ps));
+        std::vector<uint8_t> buf;
+        for (const LocalPage& lp : ix->pages) {
+            for (uint64_t r = 0; r < lp.sig; r += chunk_rows) {
+                const uint64_t nr = std::min<uint64_t>(chunk_rows, lp.sig - r);
+                buf.resize(nr * ps);
+                CK(cudaMemcpy2D(buf.data(), ps, lp.d_base + r * lp.pitch, lp.pitch, ps, nr,
+                                cudaMemcpyDeviceToHost));
+                put(buf.data(), buf.size());
+            }
+        }
     });
 }
 

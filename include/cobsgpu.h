@@ -137,6 +137,36 @@ int cobsgpu_index_open(const cobsgpu_index_desc* desc, cobsgpu_index** out);
  * header parsing (cobs/file/classic_index_header.cpp:38-50, compact_index_header.cpp:44-65) */
 int cobsgpu_index_open_file(const char* path, int device, uint32_t shard_index,
                             uint32_t shard_count, cobsgpu_index** out);
+/*
+ * Classic index construction on the device ("next" row f4 of the scope table): documents are
+ * given as in-memory sequences (a document = one or more sequences, e.g. the records of a
+ * FASTA file; k-mers are all windows of each sequence and never span two sequences).
+ * replaces: classic_construct / process_batch / process_term
+ * (cobs/construction/classic_index.cpp:39-130, 565-600), signature sizing
+ * (cobs/util/calc_signature_size.cpp:15-33).  Reading document files stays out of scope.
+ * The result is an ordinary, immediately searchable index handle.
+ */
+typedef struct cobsgpu_construct_desc {
+    uint32_t struct_size;       /* sizeof(cobsgpu_construct_desc) */
+    uint32_t term_size;
+    uint32_t canonicalize;
+    uint32_t num_hashes;
+    uint64_t signature_size;    /* rows; 0 => sized from false_positive_rate and the largest document */
+    double false_positive_rate;
+    uint32_t n_docs;
+    uint32_t n_seqs;
+    const char* const* doc_names;   /* [n_docs] */
+    const char* sequences;          /* all sequences, concatenated */
+    const uint64_t* seq_offsets;    /* [n_seqs + 1] */
+    const uint32_t* seq_doc;        /* [n_seqs] document index of every sequence */
+    int32_t device;
+    uint32_t reserved;
+} cobsgpu_construct_desc;
+
+int cobsgpu_construct_classic(const cobsgpu_construct_desc* desc, cobsgpu_index** out);
+/* writes an unsharded index in the reference's on-disk format
+ * (cobs/file/classic_index_header.cpp:26-36, cobs/file/compact_index_header.cpp:24-42) */
+int cobsgpu_index_save(const cobsgpu_index* idx, const char* path);
 void cobsgpu_index_close(cobsgpu_index* idx);
 int cobsgpu_index_get_info(const cobsgpu_index* idx, cobsgpu_index_info* out);
 /* rows of global page `page` (the header's signature_size; classic: page 0); 0 if out of range */

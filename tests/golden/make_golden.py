@@ -139,6 +139,54 @@ def main():
          [ref.random_sequence(100, 100 + i) for i in range(6)] + [ref.random_sequence(400, 9)],
          [(0.0, 0), (0.0, 10), (0.02, 0), (0.05, 7)])
 
+    # 7. construction parity (scope row f4): synthetic FASTA documents -- several records per
+    # file, wrapped lines, non-ACGT characters (hashed with zeros by the reference, not skipped),
+    # lower case, a record shorter than k, ';' comments, empty lines -- indexed by the
+    # reference's classic_construct.  The FASTA files themselves are committed as fixtures.
+    docs_dir = os.path.join(OUT, "construct_docs")
+    shutil.rmtree(docs_dir, ignore_errors=True)
+    os.makedirs(docs_dir)
+    import random
+    rnd = random.Random(11)
+
+    def seq(n, alphabet="ACGT"):
+        return "".join(rnd.choice(alphabet) for _ in range(n))
+
+    fasta_docs = {
+        "alpha": [("r1", seq(400)), ("r2", seq(95))],
+        "beta": [("only", seq(1500))],
+        "gamma": [("with_n", seq(200) + "NNNN" + seq(150) + "RY" + seq(80)), ("short", seq(20))],
+        "delta": [("lower", seq(120) + seq(60).lower() + seq(120))],
+        "epsilon": [("a", seq(31)), ("b", seq(32)), ("c", seq(30)), ("d", seq(700))],
+        "zeta": [("x", seq(64, "AC")), ("y", seq(900))],
+        "eta": [("protein", seq(300, "ACDEFGHIKLMNPQRSTVWY"))],
+        "theta": [("r", seq(333))],
+        "iota": [("r", seq(2000))],
+    }
+    for name, recs in fasta_docs.items():
+        with open(os.path.join(docs_dir, name + ".fasta"), "w") as f:
+            for i, (rn, sq) in enumerate(recs):
+                f.write(("%s%s %s\n" % (">" if i % 2 == 0 else ";", name, rn)))
+                width = 60 if i % 2 == 0 else 71
+                for j in range(0, len(sq), width):
+                    f.write(sq[j:j + width] + "\n")
+                if i % 2 == 1:
+                    f.write("\n")
+    tmp_docs = os.path.join(tmp, "construct_docs")
+    shutil.copytree(docs_dir, tmp_docs)
+    construct_cases = []
+    for tag, h, fpr, canon in (("h3", 3, 0.1, 1), ("h1", 1, 0.3, 1), ("raw", 2, 0.2, 0)):
+        f = os.path.join(tmp, "construct_%s.cobs_classic" % tag)
+        ref.classic_construct(tmp_docs, f, os.path.join(tmp, "tc_" + tag), num_hashes=h, fpr=fpr,
+                              canonicalize=canon)
+        shutil.copyfile(f, os.path.join(OUT, os.path.basename(f)))
+        construct_cases.append({"file": os.path.basename(f), "num_hashes": h,
+                                "false_positive_rate": fpr, "canonicalize": canon})
+        print("construct", tag, os.path.getsize(f))
+    for fn in os.listdir(docs_dir):      # the reference drops .cobs_cache files next to inputs
+        if fn.endswith(".cobs_cache"):
+            os.unlink(os.path.join(docs_dir, fn))
+
     # known answers for K1: canonicalisation vectors and XXH64 of k-mers
     kats = {"canonicalize": [], "xxh64": []}
     for k in (15, 31, 32, 33, 64):
@@ -156,7 +204,7 @@ def main():
         kats["canonicalize"].append({"kmer": km.decode(), "out": out.hex(), "good": good,
                                      "hex": True})
     with open(os.path.join(OUT, "golden.json"), "w") as fp:
-        json.dump({"cases": cases, "kats": kats}, fp, indent=0)
+        json.dump({"cases": cases, "kats": kats, "construct": construct_cases}, fp, indent=0)
     shutil.rmtree(tmp)
     print("wrote", os.path.join(OUT, "golden.json"))
 
