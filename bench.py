@@ -264,7 +264,9 @@ def run_ours(args):
         sig = [args.rows] * len(sig)
     index = cobs_b200.GpuIndex.procedural(cfg["kind"], cfg["n_docs"], sig, cfg["h"],
                                           page_size=cfg["page_size"], fill_seed=FILL_SEED,
-                                          device=local_rank, shard_index=rank, shard_count=world)
+                                          device=local_rank,
+                                          shard_index=rank if not args.emulate_shards else 0,
+                                          shard_count=world if not args.emulate_shards else args.emulate_shards)
     index.set_option("max_batch", max(nq, 1))
     info = index.info
     rpq = args.results_per_query
@@ -344,8 +346,21 @@ def run_ours(args):
     barrier()
     t0 = time.perf_counter()
     d2h = 0
-    for i in range(args.steps):
-        d2h = e2e_step(args.warmup + i)
+    if world == 1:
+        for i in range(args.steps):
+            d2h = e2e_step(args.warmup + i)
+    else:
+        # streaming use of the public API: two batches in flight (submit i+1, then collect i);
+        # every batch still pays its own H2D and D2H inside the timed region
+        pending = None
+        for i in range(args.steps):
+            t = sharded.submit_host(pinned[args.warmup + i], off, THRESHOLD, 0)
+            if pending is not None:
+                c, k = sharded.collect(pending)
+                d2h = c.nbytes + k.nbytes
+            pending = t
+        c, k = sharded.collect(pending)
+        d2h = c.nbytes + k.nbytes
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
@@ -419,6 +434,8 @@ def main():
     ap.add_argument("--ref-queries", type=int, default=400,
                     help="queries per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--emulate-shards", type=int, default=0,
+                    help="debug: hold shard 0 of this many document shards on one GPU")
     ap.add_argument("--no-overlap", action="store_true",
                     help="disable the cross-step pipelining (K1 prefetch, side-stream exchange)")
     args = ap.parse_args()

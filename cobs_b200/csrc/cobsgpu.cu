@@ -325,16 +325,23 @@ void build_layout(cobsgpu_index* ix, const std::vector<uint64_t>& sig) {
             ix->pages.push_back(lp);
         }
     } else {
-        // whole pages per shard, contiguous ranges balanced by bytes
-        long double total = 0;
-        for (uint32_t p = 0; p < P; ++p) total += static_cast<long double>(sig[p]) * ps;
-        long double cum = 0;
-        for (uint32_t p = 0; p < P; ++p) {
-            const long double sz = static_cast<long double>(sig[p]) * ps;
-            uint32_t owner = total > 0 ? static_cast<uint32_t>((cum + sz / 2) * S / total) : 0;
-            if (owner >= S) owner = S - 1;
-            cum += sz;
-            if (owner != g) continue;
+        // Whole pages per shard.  Every page costs the same per query k-mer (h * page_size bytes,
+        // whatever its signature_size), while its memory is signature_size * page_size: pages are
+        // sorted by size and dealt out in serpentine order, which balances the page COUNT
+        // (= work) to +-1 and the bytes (= HBM) closely.  Page sets are not contiguous; results
+        // carry global document ids, so nothing downstream cares.
+        std::vector<uint32_t> order(P);
+        for (uint32_t p = 0; p < P; ++p) order[p] = p;
+        std::stable_sort(order.begin(), order.end(),
+                         [&](uint32_t a, uint32_t b) { return sig[a] > sig[b]; });
+        std::vector<uint32_t> mine;
+        for (uint32_t i = 0; i < P; ++i) {
+            const uint32_t round = i / S, pos = i % S;
+            const uint32_t owner = (round & 1) ? S - 1 - pos : pos;
+            if (owner == g) mine.push_back(order[i]);
+        }
+        std::sort(mine.begin(), mine.end());
+        for (uint32_t p : mine) {
             LocalPage lp{};
             lp.global_page = p;
             lp.sig = sig[p];
@@ -365,7 +372,8 @@ void build_layout(cobsgpu_index* ix, const std::vector<uint64_t>& sig) {
         max_rb16 = std::max(max_rb16, lp.rb16);
         ix->shard_real_docs += lp.n_real;
         ix->bytes_per_kmer += static_cast<uint64_t>(ix->num_hashes) * lp.row_bytes;
-        ix->shard_doc_end = lp.doc_base + static_cast<uint32_t>(cols);
+        ix->shard_doc_end = std::max<uint32_t>(ix->shard_doc_end,
+                                               lp.doc_base + static_cast<uint32_t>(cols));
     }
     ix->dense_pitch = std::max<uint64_t>(128, round_up<uint64_t>(dense, 128));
     ix->ncw = std::min<uint32_t>(4, std::max<uint32_t>(1, div_ceil<uint32_t>(max_rb16, 512)));

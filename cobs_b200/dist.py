@@ -36,6 +36,9 @@ class ShardedSearch:
         self._parity = 0
         self._comm_stream = None
         self._comm_done = [None, None]
+        self._copy_stream = None
+        self._pinned = {}
+        self._pin_next = 0
 
     # -- hooks (overridden by the CPU/gloo protocol test) -------------------------------
     def _local_search(self, d_queries, off, threshold, num_results, counts, keys):
@@ -130,17 +133,48 @@ class ShardedSearch:
     def search_host(self, h_queries, off, threshold, num_results):
         """end-to-end variant: h_queries is a (pinned) host uint8 tensor; returns numpy
         (counts uint32[nq], keys uint64[nq, kmax]) on the host, kmax = longest result list."""
+        return self.collect(self.submit_host(h_queries, off, threshold, num_results))
+
+    # -- streaming: keep a few batches in flight -------------------------------------------
+    def submit_host(self, h_queries, off, threshold, num_results):
+        """Enqueue one batch end to end: H2D of the (pinned) queries, search, exchange/merge,
+        D2H of the per-query counts.  Returns a ticket for collect(); with overlap=True up to
+        two tickets may be outstanding (the buffer sets alternate)."""
         dev = torch.device("cuda", torch.cuda.current_device())
         d_q = h_queries.to(dev, non_blocking=True)
         counts, keys = self.search_device(d_q, off, threshold, num_results)
-        self.join()
-        c = counts.cpu().numpy().view(np.uint32)
-        valid = c[c != OVERFLOW]
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev, priority=-1)
+        ready = torch.cuda.Event()
+        ready.record(self._comm_stream if (self.overlap and self._comm_stream is not None)
+                     else torch.cuda.current_stream())
+        # pinned landing buffers are recycled round-robin (allocation is slow); 4 > tickets in flight
+        pool = self._pinned.setdefault(tuple(counts.shape), [])
+        if len(pool) < 4:
+            pool.append(torch.empty(counts.shape, dtype=counts.dtype, pin_memory=True))
+            h_counts = pool[-1]
+        else:
+            self._pin_next = (self._pin_next + 1) % 4
+            h_counts = pool[self._pin_next]
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(ready)
+            h_counts.copy_(counts, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self._copy_stream)
+        return {"counts": counts, "keys": keys, "h_counts": h_counts, "done": done, "d_q": d_q}
+
+    def collect(self, ticket):
+        """wait for a submitted batch; returns numpy (counts uint32[nq], keys uint64[nq, kmax])"""
+        ticket["done"].synchronize()
+        c = ticket["h_counts"].numpy().view(np.uint32)
+        valid = c[c < 0xFFFFFFFE]
         kmax = int(valid.max()) if valid.size else 0
-        kmax = min(kmax, keys.shape[1])
-        k = keys[:, :kmax].contiguous().cpu().numpy().view(np.uint64) if kmax else \
-            np.zeros((len(c), 0), dtype=np.uint64)
-        return c, k
+        kmax = min(kmax, ticket["keys"].shape[1])
+        if kmax == 0:
+            return c, np.zeros((len(c), 0), dtype=np.uint64)
+        with torch.cuda.stream(self._copy_stream):      # ordered after the counts copy
+            k = ticket["keys"][:, :kmax].contiguous().cpu()
+        return c, k.numpy().view(np.uint64)
 
 
 def shard_bounds_classic(row_size, shard_count):

@@ -74,8 +74,9 @@ typedef struct cobsgpu_index_desc {
     uint64_t fill_seed;
     int32_t device;             /* CUDA device ordinal */
     /* document-axis shard held by this handle: shard_index of shard_count.
-     * Classic: contiguous column ranges cut at multiples of 128 documents; compact:
-     * contiguous page ranges balanced by bytes.  Results carry GLOBAL document ids. */
+     * Classic: contiguous column ranges cut at multiples of 128 documents; compact: whole
+     * pages, dealt out so that page count (work) and bytes (HBM) are both balanced.
+     * Results carry GLOBAL document ids. */
     uint32_t shard_index;
     uint32_t shard_count;
     uint32_t reserved1;
@@ -93,8 +94,9 @@ typedef struct cobsgpu_index_info {
     uint64_t counts_size;   /* IndexSearchFile::counts_size() */
     uint32_t shard_index;
     uint32_t shard_count;
-    uint32_t shard_doc_begin;   /* first global column held by this shard */
-    uint32_t shard_doc_end;     /* one past the last column held (padded columns included) */
+    uint32_t shard_doc_begin;   /* lowest global column held by this shard */
+    uint32_t shard_doc_end;     /* one past the highest column held (padded columns included);
+                                   compact shards need not be contiguous in between */
     uint64_t hbm_bytes;         /* bytes of signature matrix resident on the device */
     uint64_t bytes_per_kmer;    /* algorithmic bytes per query k-mer for THIS shard:
                                    h * (unpadded row bytes held) */
