@@ -166,7 +166,7 @@ class ShardedSearch:
     def collect(self, ticket):
         """wait for a submitted batch; returns numpy (counts uint32[nq], keys uint64[nq, kmax])"""
         ticket["done"].synchronize()
-        c = ticket["h_counts"].numpy().view(np.uint32)
+        c = ticket["h_counts"].numpy().view(np.uint32).copy()   # the pinned buffer is recycled
         valid = c[c < 0xFFFFFFFE]
         kmax = int(valid.max()) if valid.size else 0
         kmax = min(kmax, ticket["keys"].shape[1])

@@ -446,3 +446,34 @@ def test_device_path_flags_invalid_bases():
             doc, score = cobs_b200.decode_keys(kk[i, :c[i]])
             assert [(0, int(d), int(s)) for d, s in zip(doc, score)] == oracle.search(o, q, 0.3, 0)
     g.close()
+
+
+def test_sharded_search_single_rank_host_api():
+    """cobs_b200.dist.ShardedSearch at world size 1: synchronous search_host and the streaming
+    submit_host / collect pair (two batches in flight) against the oracle"""
+    torch = pytest.importorskip("torch")
+    from cobs_b200.dist import ShardedSearch
+    g, o = pair(KIND_CLASSIC, 3000, [19], 3, seed=41)
+    s = ShardedSearch(g, 0, 1, results_per_query=48)
+    off = np.arange(41, dtype=np.uint64) * 100
+    batches = [[rq(100 * b + i, 100) for i in range(40)] for b in range(4)]
+    pinned = [torch.frombuffer(bytearray(b"".join(b)), dtype=torch.uint8).pin_memory()
+              for b in batches]
+
+    def check(batch, c, k, thr, lim):
+        for i, q in enumerate(batch):
+            doc, score = cobs_b200.decode_keys(k[i, :c[i]])
+            assert [(0, int(d), int(x)) for d, x in zip(doc, score)] == oracle.search(o, q, thr, lim)
+
+    c, k = s.search_host(pinned[0], off, 0.3, 0)
+    check(batches[0], c, k, 0.3, 0)
+    g.set_option("prefetch", 1)
+    tickets = []
+    for b in range(4):
+        tickets.append(s.submit_host(pinned[b], off, 0.25, 5))
+        if len(tickets) == 2:
+            c, k = s.collect(tickets.pop(0))
+            check(batches[b - 1], c, k, 0.25, 5)
+    c, k = s.collect(tickets.pop(0))
+    check(batches[3], c, k, 0.25, 5)
+    g.close()
