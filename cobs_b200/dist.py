@@ -94,7 +94,8 @@ class ShardedSearch:
         nq = len(off) - 1
         k = self.out_per_query(num_results)
         if not self.overlap:
-            b = self._buffers(nq, k, d_queries.device)
+            self._parity ^= 1
+            b = self._buffers(nq, k, d_queries.device, self._parity)
             self._local_search(d_queries, off, threshold, num_results, b["counts"], b["keys"])
             if self.world == 1:
                 return b["counts"], b["keys"][:, :k]
@@ -138,8 +139,8 @@ class ShardedSearch:
     # -- streaming: keep a few batches in flight -------------------------------------------
     def submit_host(self, h_queries, off, threshold, num_results):
         """Enqueue one batch end to end: H2D of the (pinned) queries, search, exchange/merge,
-        D2H of the per-query counts.  Returns a ticket for collect(); with overlap=True up to
-        two tickets may be outstanding (the buffer sets alternate)."""
+        D2H of the per-query counts.  Returns a ticket for collect(); up to two tickets may be
+        outstanding (the result buffers alternate between two sets)."""
         dev = torch.device("cuda", torch.cuda.current_device())
         d_q = h_queries.to(dev, non_blocking=True)
         counts, keys = self.search_device(d_q, off, threshold, num_results)
