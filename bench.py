@@ -374,6 +374,12 @@ def run_ours(args):
         with open(peaks_path) as f:
             peak = float(json.load(f)["hbm_gbs"])
         peak_src = "MEASURED_PEAKS.json hbm_gbs"
+    # DRAM bytes per K2 launch from the committed `ncu --set full` capture of this workload
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and not args.nq and not args.rows and world == 1:
+        with open(tpath) as f:
+            traffic = json.load(f).get(args.workload, {}).get("dram_bytes_per_launch")
     k2_ms = float(score_ms.item())
     algo_bytes_per_launch = info.bytes_per_kmer * kmers_per_step   # this rank's shard
     achieved = algo_bytes_per_launch / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else 0.0
@@ -402,7 +408,7 @@ def run_ours(args):
                        "results_last_step": n_results},
             "queries_per_s": value / T,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "kernel": "score_kernel<%d,CAND>" % cfg["h"],
+                         "frac": achieved / peak, "traffic": traffic, "kernel": "score_kernel<%d,CAND>" % cfg["h"],
                          "kernel_ms": k2_ms, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo_bytes_per_launch,
                          "whole_step_frac": (bytes_per_kmer / world) * value / 1e9 / peak},

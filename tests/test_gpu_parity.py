@@ -477,3 +477,53 @@ def test_sharded_search_single_rank_host_api():
     c, k = s.collect(tickets.pop(0))
     check(batches[3], c, k, 0.25, 5)
     g.close()
+
+
+def test_very_long_queries_like_the_reference_tests():
+    """tests/classic_index_query.cpp:27 queries a 50 000-bp sequence (the reference's 16-bit
+    score path); 70 000 bp crosses into its 32-bit path.  Here both run through the u32
+    accumulation of the score kernel (flush every 248 k-mers)."""
+    g, o = pair(KIND_CLASSIC, 33, [4001], 3, seed=50)
+    gc, oc = pair(KIND_COMPACT, 40, [1500, 900, 2100], 3, page_size=2, seed=51)
+    for L in (50_000, 70_000):
+        q = rq(L, L)
+        assert np.array_equal(g.scores([q])[0], o.scores(q))
+        assert as_list(g.search_batch([q], 0.0, 0)[0]) == oracle.search(o, q, 0.0, 0)
+        assert as_list(g.search_batch([q], 0.5, 3)[0]) == oracle.search(o, q, 0.5, 3)
+        assert as_list(gc.search_batch([q], 0.2, 0)[0]) == oracle.search(oc, q, 0.2, 0)
+    # mixed batch: short and very long queries together
+    qs = [rq(1, 100), rq(2, 20_000), rq(3, 31), rq(4, 286)]
+    for q, r in zip(qs, g.search_batch(qs, 0.3, 0)):
+        assert as_list(r) == oracle.search(o, q, 0.3, 0)
+    g.close()
+    gc.close()
+
+
+def test_randomised_differential_against_oracle():
+    """seeded random geometries x random batches: K1+K2+K3 through the C ABI == oracle"""
+    rng = np.random.default_rng(2026)
+    for it in range(12):
+        kind = int(rng.integers(0, 2))
+        h = int(rng.integers(1, 5))
+        k = int(rng.choice([15, 21, 31, 32]))
+        canon = int(rng.integers(0, 2))
+        if kind == KIND_CLASSIC:
+            n_docs = int(rng.integers(1, 6000))
+            sig, ps = [int(rng.integers(3, 400))], 0
+        else:
+            ps = int(rng.choice([1, 2, 5, 16, 40, 300]))
+            pages = int(rng.integers(1, 6))
+            n_docs = int(rng.integers(8 * ps * (pages - 1) + 1, 8 * ps * pages + 1))
+            sig = [int(x) for x in rng.integers(3, 300, size=pages)]
+        g, o = pair(kind, n_docs, sig, h, page_size=ps, k=k, canon=canon, seed=it)
+        queries = [rq(1000 * it + i, int(L)) for i, L in enumerate(rng.integers(k, 350, size=9))]
+        thr = float(rng.choice([0.0, 0.05, 0.2, 0.6]))
+        lim = int(rng.choice([0, 1, 4, 50]))
+        got_scores = g.scores(queries)
+        got = g.search_batch(queries, thr, lim)
+        for q, sc, r in zip(queries, got_scores, got):
+            assert np.array_equal(sc, o.scores(q)), (it, kind, n_docs, sig, ps, h, k)
+            if h == 1 and len(q) == k:
+                continue
+            assert as_list(r) == oracle.search(o, q, thr, lim), (it, thr, lim)
+        g.close()
