@@ -245,7 +245,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import cobs_b200
-    from cobs_b200.dist import ShardedSearch
+    from cobs_b200.dist import QuerySplitSearch, ShardedSearch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -262,15 +262,18 @@ def run_ours(args):
     sig = cfg["sig"]
     if args.rows:
         sig = [args.rows] * len(sig)
+    split_queries = args.parallelism == "queries" and world > 1
     index = cobs_b200.GpuIndex.procedural(cfg["kind"], cfg["n_docs"], sig, cfg["h"],
                                           page_size=cfg["page_size"], fill_seed=FILL_SEED,
                                           device=local_rank,
-                                          shard_index=rank if not args.emulate_shards else 0,
-                                          shard_count=world if not args.emulate_shards else args.emulate_shards)
+                                          shard_index=0 if (args.emulate_shards or split_queries) else rank,
+                                          shard_count=args.emulate_shards if args.emulate_shards
+                                          else (1 if split_queries else world))
     index.set_option("max_batch", max(nq, 1))
     info = index.info
     rpq = args.results_per_query
-    sharded = ShardedSearch(index, rank, world, rpq, overlap=not args.no_overlap)
+    cls = QuerySplitSearch if split_queries else ShardedSearch
+    sharded = cls(index, rank, world, rpq, overlap=not args.no_overlap)
 
     # bytes per k-mer of the WHOLE index (h * ceil(N/8), unpadded reference layout)
     if cfg["kind"] == 0:
@@ -329,7 +332,7 @@ def run_ours(args):
     launches = tm["kernel_launches"] + (args.steps if world > 1 else 0)
     index.set_option("timing", 0)
     index.set_option("inputs_ready", 0)     # the e2e leg uploads its queries itself
-    n_results = int((last[0].cpu().numpy().view(np.uint32) % 0xFFFFFFFF).sum())
+    n_results = int((last[0].cpu().numpy().view(np.uint32).reshape(-1) % 0xFFFFFFFE).sum())
 
     # ---- leg 2: end to end from host buffers through the public API ("e2e") ----
     h2d = int(pinned[0].numel() + off.nbytes)
@@ -381,7 +384,11 @@ def run_ours(args):
         with open(tpath) as f:
             traffic = json.load(f).get(args.workload, {}).get("dram_bytes_per_launch")
     k2_ms = float(score_ms.item())
-    algo_bytes_per_launch = info.bytes_per_kmer * kmers_per_step   # this rank's shard
+    # this rank's share of a step: its document shard, or its slice of the queries
+    algo_bytes_per_launch = info.bytes_per_kmer * kmers_per_step
+    if split_queries:
+        per = (nq + world - 1) // world
+        algo_bytes_per_launch = info.bytes_per_kmer * per * T
     achieved = algo_bytes_per_launch / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else 0.0
 
     if rank == 0:
@@ -399,8 +406,11 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": args.workload + ": " + cfg["desc"],
-                       "parallelism": "document-axis shards x%d, NCCL all-gather of per-rank "
-                                      "result blocks" % world if world > 1 else "single GPU",
+                       "parallelism": ("single GPU" if world == 1 else
+                                       "index replicated x%d, queries split, NCCL all-gather of "
+                                       "the result blocks" % world if split_queries else
+                                       "document-axis shards x%d, NCCL all-gather of per-rank "
+                                       "result blocks + merge" % world),
                        "queries_per_step": nq, "kmers_per_query": T,
                        "bytes_per_kmer": bytes_per_kmer, "hbm_bytes_this_rank": info.hbm_bytes,
                        "l2_policy": "each step a different batch; rows touched per step "
@@ -440,6 +450,9 @@ def main():
     ap.add_argument("--ref-queries", type=int, default=400,
                     help="queries per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parallelism", default="docs", choices=["docs", "queries"],
+                    help="N > 1: shard the document axis (default, BASELINE.json's north_star) or "
+                         "replicate the index and split every query batch")
     ap.add_argument("--emulate-shards", type=int, default=0,
                     help="debug: hold shard 0 of this many document shards on one GPU")
     ap.add_argument("--no-overlap", action="store_true",

@@ -162,20 +162,70 @@ class ShardedSearch:
             h_counts.copy_(counts, non_blocking=True)
             done = torch.cuda.Event()
             done.record(self._copy_stream)
-        return {"counts": counts, "keys": keys, "h_counts": h_counts, "done": done, "d_q": d_q}
+        return {"counts": counts, "keys": keys, "h_counts": h_counts, "done": done, "d_q": d_q,
+                "nq": len(off) - 1}
 
     def collect(self, ticket):
         """wait for a submitted batch; returns numpy (counts uint32[nq], keys uint64[nq, kmax])"""
         ticket["done"].synchronize()
-        c = ticket["h_counts"].numpy().view(np.uint32).copy()   # the pinned buffer is recycled
+        nq = ticket["nq"]
+        # the pinned buffer is recycled: copy; [world, per] layouts flatten to query order
+        c = ticket["h_counts"].numpy().view(np.uint32).reshape(-1)[:nq].copy()
         valid = c[c < 0xFFFFFFFE]
         kmax = int(valid.max()) if valid.size else 0
-        kmax = min(kmax, ticket["keys"].shape[1])
+        kmax = min(kmax, ticket["keys"].shape[-1])
         if kmax == 0:
-            return c, np.zeros((len(c), 0), dtype=np.uint64)
+            return c, np.zeros((nq, 0), dtype=np.uint64)
         with torch.cuda.stream(self._copy_stream):      # ordered after the counts copy
-            k = ticket["keys"][:, :kmax].contiguous().cpu()
-        return c, k.numpy().view(np.uint64)
+            k = ticket["keys"][..., :kmax].contiguous().cpu()
+        return c, k.numpy().view(np.uint64).reshape(-1, kmax)[:nq]
+
+
+class QuerySplitSearch(ShardedSearch):
+    """The other way to use several GPUs, for an index that fits into one GPU's HBM: every rank
+    holds the WHOLE index and searches its contiguous slice of each query batch; the per-rank
+    result blocks are all-gathered, which already is the batch in query order -- no merge.
+    (BASELINE.json's north_star shards the document axis "where the matrix overflows one GPU";
+    below that size replicas keep the long row slices that the score kernel likes best.)"""
+
+    def search_device(self, d_queries, off, threshold, num_results):
+        nq = len(off) - 1
+        k = self.out_per_query(num_results)
+        if self.world == 1:
+            return super().search_device(d_queries, off, threshold, num_results)
+        per = (nq + self.world - 1) // self.world
+        lo = min(self.rank * per, nq)
+        hi = min(lo + per, nq)
+        self._parity ^= 1
+        par = self._parity
+        b = self._buffers(per, k, d_queries.device, par)
+        main = torch.cuda.current_stream() if self.overlap else None
+        if self.overlap and self._comm_done[par] is not None:
+            main.wait_event(self._comm_done[par])
+        if hi < lo + per:
+            b["counts"].zero_()                       # ragged last rank: unused slots stay empty
+        if hi > lo:
+            n = hi - lo
+            self._local_search(d_queries, off[lo:hi + 1], threshold, num_results,
+                               b["counts"][:n], b["keys"][:n])
+        if not self.overlap:
+            dist.all_gather_into_tensor(b["gathered"], b["block"], group=self.group)
+        else:
+            if self._comm_stream is None:
+                self._comm_stream = torch.cuda.Stream(device=d_queries.device, priority=-1)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            with torch.cuda.stream(self._comm_stream):
+                self._comm_stream.wait_event(ready)
+                dist.all_gather_into_tensor(b["gathered"], b["block"], group=self.group)
+                done = torch.cuda.Event()
+                done.record(self._comm_stream)
+            self._comm_done[par] = done
+        # rank-major == query order: query q lives at [q // per][q % per]; collect() flattens
+        return b["all_counts"], b["all_keys"]
+
+    def out_per_query(self, num_results):
+        return self.rpq if num_results == 0 else min(num_results, self.rpq)
 
 
 def shard_bounds_classic(row_size, shard_count):

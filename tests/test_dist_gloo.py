@@ -102,6 +102,30 @@ def _worker(rank, world, port, ret):
     gathered = [None] * world
     dist.all_gather_object(gathered, (counts.numpy().tobytes(), valid))
     ok &= all(g == gathered[0] for g in gathered)
+    # ---- replicas: every rank holds all columns and searches its slice of the batch ----
+    from cobs_b200.dist import QuerySplitSearch
+
+    class CpuReplica(QuerySplitSearch):
+        def _local_search(self, d_queries, off, threshold, num_results, counts, keys):
+            blob = bytes(d_queries.numpy())
+            for i in range(len(off) - 1):
+                q = blob[int(off[i]):int(off[i + 1])]
+                res = oracle.search(o, q, threshold, num_results)[:self.rpq]
+                counts[i] = len(res)
+                for j, (_, d, sc_) in enumerate(res):
+                    keys[i, j] = int(np.int64(_key(sc_, d).view(np.int64)))
+
+    r = CpuReplica(None, rank, world, 64)
+    odd = queries[:11]                      # 11 queries over 2 ranks: ragged last slice
+    blob = torch.frombuffer(bytearray(b"".join(odd)), dtype=torch.uint8)
+    off = np.arange(len(odd) + 1, dtype=np.uint64) * 100
+    counts, keys = r.search_device(blob, off, 0.12, 7)
+    c = counts.numpy().view(np.uint32).reshape(-1)[:len(odd)]
+    kk = keys.numpy().view(np.uint64).reshape(-1, keys.shape[-1])[:len(odd)]
+    for i, q in enumerate(odd):
+        got = [(0, int(x & np.uint64(0xFFFFFFFF)),
+                int(~(x >> np.uint64(32)) & np.uint64(0xFFFFFFFF))) for x in kk[i, :c[i]]]
+        ok &= got == oracle.search(o, q, 0.12, 7)
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 
