@@ -16,6 +16,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cerrno>
 #include <cstring>
 #include <functional>
@@ -125,7 +126,7 @@ struct LocalPage {
     uint8_t* d_base;
 };
 
-enum Phase { PH_H2D = 0, PH_HASH, PH_SCORE, PH_SELECT, PH_D2H, PH_COUNT };
+enum Phase { PH_H2D = 0, PH_HASH, PH_SCORE, PH_SELECT, PH_D2H };
 
 }  // namespace
 
@@ -196,7 +197,7 @@ struct cobsgpu_index {
         int occupancy = 0;
     } score_cfg[3];
     DevBuf d_cand, d_scratch, d_cand_count, d_res_count, d_offsets, d_out_doc, d_out_score, d_dense;
-    PinBuf h_stage, h_off, h_doc, h_score, h_counts, h_dense;
+    PinBuf h_off, h_doc, h_score, h_counts, h_dense;
     // current batch (host copies)
     std::vector<uint64_t> b_qoff;
     std::vector<uint32_t> b_koff, b_thr;
@@ -553,7 +554,11 @@ void launch_score(cobsgpu_index* ix, ScoreParams sp, int mode, cudaStream_t st) 
         // when a stage (h row slices) is large
         const size_t avail = ix->smem_optin;   // 227 KB on B200
         uint32_t ns = 0;
-        for (int occ = 3; occ >= 1; --occ) {
+        // tuning knobs for experiments: COBSGPU_OCC (CTAs per SM to aim for), COBSGPU_STAGES (cap)
+        const char* e_occ = std::getenv("COBSGPU_OCC");
+        const char* e_st = std::getenv("COBSGPU_STAGES");
+        const int occ0 = e_occ ? std::max(1, std::min(4, std::atoi(e_occ))) : 3;
+        for (int occ = occ0; occ >= 1; --occ) {
             const size_t budget = avail / occ - (occ > 1 ? 1024 : 0);
             if (budget <= 2048 + stage) continue;
             ns = static_cast<uint32_t>((budget - 2048) / stage);
@@ -561,6 +566,7 @@ void launch_score(cobsgpu_index* ix, ScoreParams sp, int mode, cudaStream_t st) 
         }
         if (ns == 0) throw Err{ COBSGPU_ERR_INVALID_ARG, "num_hashes too large for shared memory" };
         ns = std::min<uint32_t>(ns, 64);
+        if (e_st) ns = std::max<uint32_t>(1, std::min<uint32_t>(ns, static_cast<uint32_t>(std::atoi(e_st))));
         cfg.n_stages = ns;
         cfg.smem = score_smem_header(ns) + static_cast<size_t>(ns) * stage;
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -759,7 +765,7 @@ void run_pass(cobsgpu_index* ix, const uint32_t* d_qlist, uint32_t n_slots, uint
     result_counts_kernel<<<div_ceil<uint32_t>(n_slots, 256), 256, 0, st>>>(
         sp.cand_count, n_slots, cap, limit, ix->d_res_count.as<uint32_t>(), ix->d_flags() + 1);
     CK(cudaGetLastError());
-    sort_small_kernel<<<n_slots, SORT_SMALL_THREADS, 0, st>>>(sp.cand, sp.cand_count, cap, 1);
+    sort_small_kernel<<<n_slots, SORT_SMALL_THREADS, 0, st>>>(sp.cand, sp.cand_count, cap);
     CK(cudaGetLastError());
     ix->tm.kernel_launches += 2;
     *large_in_scratch = false;

@@ -78,7 +78,6 @@ static constexpr uint32_t SCORE_ITEM_Q = 2;   // item ids the producer may run a
 
 static constexpr int SCORE_MAX_THREADS = 160;   // 4 consumer warps + 1 producer warp
 static constexpr int SCORE_PLANES = 8;          // counts up to 255 between flushes
-static constexpr uint32_t SCORE_FLUSH = 248;    // k-mers per DENSE32 flush (multiple of 8)
 
 // full adder over 32 lanes of documents
 #define COBS_CSA(sum, carry, a, b, c)            \

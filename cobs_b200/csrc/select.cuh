@@ -149,13 +149,12 @@ __global__ void __launch_bounds__(1024) scan_offsets_kernel(const uint32_t* res_
 
 // one CTA per query: sort the (<= SORT_SMALL_MAX) candidates in shared memory, in place.
 __global__ void __launch_bounds__(SORT_SMALL_THREADS)
-sort_small_kernel(uint64_t* cand, const uint32_t* cand_count, uint32_t cap, uint32_t total_hashes_gt1) {
+sort_small_kernel(uint64_t* cand, const uint32_t* cand_count, uint32_t cap) {
     __shared__ uint64_t s[SORT_SMALL_MAX];
     const uint32_t qi = blockIdx.x;
     uint32_t n = cand_count[qi];
     if (n > cap) n = cap;
     if (n < 2 || n > SORT_SMALL_MAX) return;
-    (void)total_hashes_gt1;
     uint64_t* keys = cand + static_cast<uint64_t>(qi) * cap;
     const uint32_t np2 = next_pow2(n);
     for (uint32_t i = threadIdx.x; i < np2; i += blockDim.x) s[i] = i < n ? keys[i] : KEY_PAD;
