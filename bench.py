@@ -346,6 +346,10 @@ def run_ours(args):
             return c.nbytes + k.nbytes
     for i in range(args.warmup):
         e2e_step(i)
+    if world > 1:   # warm the streaming pattern too (both buffer sets, side streams)
+        tk = [sharded.submit_host(pinned[i], off, THRESHOLD, 0) for i in range(2)]
+        for t in tk:
+            sharded.collect(t)
     barrier()
     t0 = time.perf_counter()
     d2h = 0

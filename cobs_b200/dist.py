@@ -150,13 +150,12 @@ class ShardedSearch:
         ready.record(self._comm_stream if (self.overlap and self._comm_stream is not None)
                      else torch.cuda.current_stream())
         # pinned landing buffers are recycled round-robin (allocation is slow); 4 > tickets in flight
-        pool = self._pinned.setdefault(tuple(counts.shape), [])
-        if len(pool) < 4:
-            pool.append(torch.empty(counts.shape, dtype=counts.dtype, pin_memory=True))
-            h_counts = pool[-1]
-        else:
-            self._pin_next = (self._pin_next + 1) % 4
-            h_counts = pool[self._pin_next]
+        pool = self._pinned.get(tuple(counts.shape))
+        if pool is None:     # all four at once, on first use (pinned allocation is slow)
+            pool = [torch.empty(counts.shape, dtype=counts.dtype, pin_memory=True) for _ in range(4)]
+            self._pinned[tuple(counts.shape)] = pool
+        self._pin_next = (self._pin_next + 1) % 4
+        h_counts = pool[self._pin_next]
         with torch.cuda.stream(self._copy_stream):
             self._copy_stream.wait_event(ready)
             h_counts.copy_(counts, non_blocking=True)
