@@ -347,7 +347,7 @@ def run_ours(args):
     for i in range(args.warmup):
         e2e_step(i)
     if world > 1:   # warm the streaming pattern too (both buffer sets, side streams)
-        tk = [sharded.submit_host(pinned[i], off, THRESHOLD, 0) for i in range(2)]
+        tk = [sharded.submit_host(pinned[i], off, THRESHOLD, 0) for i in range(sharded.depth - 1)]
         for t in tk:
             sharded.collect(t)
     barrier()
@@ -357,17 +357,17 @@ def run_ours(args):
         for i in range(args.steps):
             d2h = e2e_step(args.warmup + i)
     else:
-        # streaming use of the public API: two batches in flight (submit i+1, then collect i);
-        # every batch still pays its own H2D and D2H inside the timed region
-        pending = None
+        # streaming use of the public API: up to three batches in flight (submit ahead, collect
+        # in order); every batch still pays its own H2D and D2H inside the timed region
+        pending = []
         for i in range(args.steps):
-            t = sharded.submit_host(pinned[args.warmup + i], off, THRESHOLD, 0)
-            if pending is not None:
-                c, k = sharded.collect(pending)
+            pending.append(sharded.submit_host(pinned[args.warmup + i], off, THRESHOLD, 0))
+            if len(pending) == sharded.depth - 1:
+                c, k = sharded.collect(pending.pop(0))
                 d2h = c.nbytes + k.nbytes
-            pending = t
-        c, k = sharded.collect(pending)
-        d2h = c.nbytes + k.nbytes
+        while pending:
+            c, k = sharded.collect(pending.pop(0))
+            d2h = c.nbytes + k.nbytes
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:

@@ -22,20 +22,22 @@ class ShardedSearch:
     All ranks must call search_device() with the same queries; every rank ends up with the
     same merged result."""
 
-    def __init__(self, index, rank=0, world=1, results_per_query=64, group=None, overlap=False):
+    def __init__(self, index, rank=0, world=1, results_per_query=64, group=None, overlap=False,
+                 depth=4):
         """overlap=True (world > 1): the all-gather + merge of a call run on a side stream and
-        alternate between two buffer sets, so they overlap the next call's score kernel.  The
-        returned tensors are then only valid after join() / synchronize()."""
+        rotate through `depth` buffer sets, so they overlap the next call's score kernel.  The
+        returned tensors are then only valid after join()."""
         self.index = index
         self.rank = rank
         self.world = world
         self.rpq = results_per_query
         self.group = group
         self.overlap = bool(overlap) and world > 1
-        self._bufs = {}
+        self.depth = max(2, int(depth))      # result-buffer sets in rotation: depth - 1 batches
+        self._bufs = {}                      # may be in flight (submit_host) at any time
         self._parity = 0
         self._comm_stream = None
-        self._comm_done = [None, None]
+        self._comm_done = [None] * self.depth
         self._copy_stream = None
         self._pinned = {}
         self._pin_next = 0
@@ -94,7 +96,7 @@ class ShardedSearch:
         nq = len(off) - 1
         k = self.out_per_query(num_results)
         if not self.overlap:
-            self._parity ^= 1
+            self._parity = (self._parity + 1) % self.depth
             b = self._buffers(nq, k, d_queries.device, self._parity)
             self._local_search(d_queries, off, threshold, num_results, b["counts"], b["keys"])
             if self.world == 1:
@@ -107,7 +109,7 @@ class ShardedSearch:
         # pipelined: local search on the current stream, exchange + merge on a side stream
         if self._comm_stream is None:
             self._comm_stream = torch.cuda.Stream(device=d_queries.device, priority=-1)
-        self._parity ^= 1
+        self._parity = (self._parity + 1) % self.depth
         par = self._parity
         b = self._buffers(nq, k, d_queries.device, par)
         main = torch.cuda.current_stream()
@@ -139,8 +141,8 @@ class ShardedSearch:
     # -- streaming: keep a few batches in flight -------------------------------------------
     def submit_host(self, h_queries, off, threshold, num_results):
         """Enqueue one batch end to end: H2D of the (pinned) queries, search, exchange/merge,
-        D2H of the per-query counts.  Returns a ticket for collect(); up to two tickets may be
-        outstanding (the result buffers alternate between two sets)."""
+        D2H of the per-query counts.  Returns a ticket for collect(); up to depth - 1 tickets
+        may be outstanding (the result buffers rotate through `depth` sets)."""
         dev = torch.device("cuda", torch.cuda.current_device())
         d_q = h_queries.to(dev, non_blocking=True)
         counts, keys = self.search_device(d_q, off, threshold, num_results)
@@ -195,7 +197,7 @@ class QuerySplitSearch(ShardedSearch):
         per = (nq + self.world - 1) // self.world
         lo = min(self.rank * per, nq)
         hi = min(lo + per, nq)
-        self._parity ^= 1
+        self._parity = (self._parity + 1) % self.depth
         par = self._parity
         b = self._buffers(per, k, d_queries.device, par)
         main = torch.cuda.current_stream() if self.overlap else None
