@@ -23,7 +23,7 @@ struct HashParams {
     uint32_t canonicalize;
     uint64_t* hashes;         // device [total_kmers * h]
     int* first_bad;           // device: min query index holding a non-ACGT base (canonical only)
-    uint32_t* bad;            // device [nq], zero-initialised: set to 1 for such queries
+    uint32_t* bad;            // device [nq], armed to 0x7F7F7F7F: set to 1 for such queries
 };
 
 namespace xxh {

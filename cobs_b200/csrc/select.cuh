@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherParams p) {
         for (uint32_t i = threadIdx.x; i < r && i < p.stride; i += blockDim.x) o[i] = keys[i];
         // more candidates than slots: the list would be incomplete -> flagged, never silent
         if (threadIdx.x == 0)
-            p.out_counts[q] = (p.bad && p.bad[q]) ? COUNT_INVALID
+            p.out_counts[q] = (p.bad && p.bad[q] == 1) ? COUNT_INVALID
                               : p.cand_count[qi] > p.cap ? COUNT_OVERFLOW
                                                          : (r < p.stride ? r : p.stride);
     } else {
@@ -312,7 +312,7 @@ static constexpr uint32_t FIN_WARPS = 8;
 struct FinalizeParams {
     const uint64_t* cand;
     const uint32_t* cand_count;
-    const uint32_t* bad;    // [nq] != 0: query holds a non-ACGT base (canonicalising index)
+    const uint32_t* bad;    // [nq] == 1: query holds a non-ACGT base (canonicalising index)
     uint32_t cap;
     uint32_t nq;
     uint64_t limit;
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_strided_kernel(Finali
         n = c < p.cap ? c : p.cap;
         r = (p.limit != 0 && n > p.limit) ? static_cast<uint32_t>(p.limit) : n;
         if (r > p.stride) r = p.stride;
-        const bool invalid = p.bad[q] != 0;
+        const bool invalid = p.bad[q] == 1;
         if (lane == 0) p.out_counts[q] = invalid ? COUNT_INVALID : (c > p.cap ? COUNT_OVERFLOW : r);
         if (c > p.cap || invalid) n = 0;   // flagged: the list would be incomplete / meaningless
         if (n > 32) {

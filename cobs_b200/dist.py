@@ -116,17 +116,23 @@ class ShardedSearch:
         if self._comm_done[par] is not None:
             main.wait_event(self._comm_done[par])      # buffer set free again
         self._local_search(d_queries, off, threshold, num_results, b["counts"], b["keys"])
-        ready = torch.cuda.Event()
+        ready, done = self._events(b)
         ready.record(main)
         with torch.cuda.stream(self._comm_stream):
             self._comm_stream.wait_event(ready)
             dist.all_gather_into_tensor(b["gathered"], b["block"], group=self.group)
             self._merge(b["all_counts"], b["all_keys"], num_results, b["out_counts"],
                         b["out_keys"])
-            done = torch.cuda.Event()
             done.record(self._comm_stream)
         self._comm_done[par] = done
         return b["out_counts"], b["out_keys"]
+
+    @staticmethod
+    def _events(b):
+        """the (ready, done) event pair of a buffer set, created once and re-recorded"""
+        if "ev" not in b:
+            b["ev"] = (torch.cuda.Event(), torch.cuda.Event())
+        return b["ev"]
 
     def join(self):
         """make the current stream wait for the pending exchange/merge work"""
@@ -214,12 +220,11 @@ class QuerySplitSearch(ShardedSearch):
         else:
             if self._comm_stream is None:
                 self._comm_stream = torch.cuda.Stream(device=d_queries.device, priority=-1)
-            ready = torch.cuda.Event()
+            ready, done = self._events(b)
             ready.record(main)
             with torch.cuda.stream(self._comm_stream):
                 self._comm_stream.wait_event(ready)
                 dist.all_gather_into_tensor(b["gathered"], b["block"], group=self.group)
-                done = torch.cuda.Event()
                 done.record(self._comm_stream)
             self._comm_done[par] = done
         # rank-major == query order: query q lives at [q // per][q % per]; collect() flattens
