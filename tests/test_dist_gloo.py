@@ -102,6 +102,48 @@ def _worker(rank, world, port, ret):
     gathered = [None] * world
     dist.all_gather_object(gathered, (counts.numpy().tobytes(), valid))
     ok &= all(g == gathered[0] for g in gathered)
+    # ---- the pipelined control flow (overlap=True) with stand-ins for the CUDA stream API:
+    # ring of buffer sets, two-batch throttle, side-stream exchange.  Results of several
+    # consecutive batches must all be right and must not clobber each other. ----
+    import contextlib
+
+    class _FakeEvent:
+        def record(self, stream=None):
+            pass
+
+        def synchronize(self):
+            pass
+
+    class _FakeStream:
+        def __init__(self, *a, **kw):
+            pass
+
+        def wait_event(self, ev):
+            pass
+
+        def wait_stream(self, st):
+            pass
+
+    torch.cuda.Event = _FakeEvent
+    torch.cuda.Stream = _FakeStream
+    torch.cuda.current_stream = lambda *a, **kw: _FakeStream()
+    torch.cuda.stream = lambda st: contextlib.nullcontext()
+    p = CpuShard(None, rank, world, RPQ, overlap=True, depth=3)
+    outs = []
+    for step in range(5):
+        qs = queries[step:step + 4]
+        bl = torch.frombuffer(bytearray(b"".join(qs)), dtype=torch.uint8)
+        of = np.arange(len(qs) + 1, dtype=np.uint64) * 100
+        c_, k_ = p.search_device(bl, of, 0.12, 5)
+        outs.append((qs, c_.numpy().view(np.uint32).copy(), k_.numpy().view(np.uint64).copy()))
+        ok &= len(p._recent_done) <= 3      # pruned to the last two at every call
+    p.join()
+    for qs, c_, k_ in outs:
+        for i, q in enumerate(qs):
+            got = [(0, int(x & np.uint64(0xFFFFFFFF)),
+                    int(~(x >> np.uint64(32)) & np.uint64(0xFFFFFFFF))) for x in k_[i, :c_[i]]]
+            ok &= got == oracle.search(o, q, 0.12, 5)
+
     # ---- replicas: every rank holds all columns and searches its slice of the batch ----
     from cobs_b200.dist import QuerySplitSearch
 
