@@ -19,15 +19,12 @@ public:
     ClassicSearch(std::shared_ptr<IndexSearchFile> index);
     ClassicSearch(std::vector<std::shared_ptr<IndexSearchFile> > indices);
 
-    void search(
-        const std::string& query,
-        std::vector<SearchResult>& result,
-        double threshold = 0.0, size_t num_results = 0) final;
+    void search(const std::string& query, std::vector<SearchResult>& result,
+                double threshold = 0.0, size_t num_results = 0) final;
 
-    void search_batch(
-        const std::vector<std::string>& queries,
-        std::vector<std::vector<SearchResult> >& results,
-        double threshold = 0.0, size_t num_results = 0) final;
+    void search_batch(const std::vector<std::string>& queries,
+                      std::vector<std::vector<SearchResult> >& results,
+                      double threshold = 0.0, size_t num_results = 0) final;
 
 protected:
     std::vector<std::shared_ptr<IndexSearchFile> > index_files_;
