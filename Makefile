@@ -21,7 +21,7 @@ HOST_INC  := -Icobs_b200/host/include -Iinclude
 HOST_FLAGS := -std=c++17 -O2 -Wall -fPIC $(HOST_INC)
 
 ifneq ($(wildcard cobs_b200/host/src/*.cpp),)
-host: build/libcobs_b200.so build/cobs build/host_tests
+host: build/libcobs_b200.so build/cobs build/host_tests build/host_unit_tests
 else
 host:
 	@echo 'host sources not present yet'
@@ -37,6 +37,10 @@ build/cobs: cobs_b200/host/cli/cobs_main.cpp build/libcobs_b200.so
 	    -Wl,-rpath,'$$ORIGIN' -Wl,-rpath,'$$ORIGIN/../cobs_b200/lib'
 
 build/host_tests: cobs_b200/host/tests/host_tests.cpp build/libcobs_b200.so
+	$(CXX) $(HOST_FLAGS) -o $@ $< -Lbuild -lcobs_b200 -Lcobs_b200/lib -lcobsgpu \
+	    -Wl,-rpath,'$$ORIGIN' -Wl,-rpath,'$$ORIGIN/../cobs_b200/lib'
+
+build/host_unit_tests: cobs_b200/host/tests/host_unit_tests.cpp build/libcobs_b200.so
 	$(CXX) $(HOST_FLAGS) -o $@ $< -Lbuild -lcobs_b200 -Lcobs_b200/lib -lcobsgpu \
 	    -Wl,-rpath,'$$ORIGIN' -Wl,-rpath,'$$ORIGIN/../cobs_b200/lib'
 

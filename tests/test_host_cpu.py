@@ -12,8 +12,22 @@ COBS = os.path.join(ROOT, "build", "cobs")
 
 
 def test_binaries_built():
-    for f in ("cobs", "host_tests", "libcobs_b200.so"):
+    for f in ("cobs", "host_tests", "host_unit_tests", "libcobs_b200.so"):
         assert os.path.exists(os.path.join(ROOT, "build", f)), f
+
+
+def test_host_unit_tests_binary():
+    """Timer, header sniffing, error conventions of the C++ mirror (no GPU needed)"""
+    exe = os.path.join(ROOT, "build", "host_unit_tests")
+    r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden")], stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "host_unit_tests: ok" in r.stdout
+    # assert_exit: message on stderr + exit(EXIT_FAILURE) (cobs/util/error_handling.cpp:19-28)
+    r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden"), "exit_error"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1
+    assert r.stderr.strip() == "query too short, needs to be at least 31 characters long"
 
 
 def test_usage_and_version():
