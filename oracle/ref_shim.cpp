@@ -23,6 +23,7 @@
 #include <cobs/util/query.hpp>
 
 #include <tlx/die.hpp>
+#include <tlx/logger/core.hpp>
 #include <xxhash.h>
 
 #include <chrono>
@@ -46,6 +47,10 @@ thread_local std::string g_error;
 
 template <typename F>
 int guarded(F&& f) {
+    // like the reference's main() (src/cobs.cpp:1058): log lines go to stderr, stdout stays
+    // clean for the one JSON line bench.py prints
+    static bool once = (tlx::set_logger_to_stderr(), true);
+    (void)once;
     tlx::set_die_with_exception(true);
     try {
         f();
