@@ -64,6 +64,29 @@ THRESHOLD = 0.8
 FILL_SEED = 20260101
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything but the result line goes to stderr: libraries (NCCL prints its version line on
+    stdout, the reference logs through tlx) must not pollute the ONE JSON line of the contract."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
+
+
 def make_batch(seed, nq):
     """nq random ACGT queries of QUERY_LEN bp as one uint8 blob + offsets"""
     rng = np.random.default_rng(seed)
@@ -235,7 +258,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -434,7 +457,7 @@ def run_ours(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     index.close()
     if world > 1:
         dist.destroy_process_group()
@@ -463,6 +486,7 @@ def main():
                     help="disable the cross-step pipelining (K1 prefetch, side-stream exchange)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
