@@ -9,11 +9,14 @@
 #include <cobs/util/error_handling.hpp>
 #include <cobs/util/file.hpp>
 
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <map>
 #include <memory>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -146,12 +149,104 @@ int query(int argc, char** argv) {
     return 0;
 }
 
+// `cobs benchmark-fpr`: the reference's micro-benchmark of the query path
+// (src/cobs.cpp:605-730): mt19937-seeded random queries of num_kmers + 30 bp, warm-up, then a
+// loop of search() with threshold 0 / all results, and a "RESULT name=benchmark ..." line.
+// --batch N (extension) sends N queries per GPU batch instead of one search() per query.
+int benchmark_fpr(int argc, char** argv) {
+    std::string in_file;
+    unsigned num_kmers = 1000, num_queries = 10000, num_warmup = 100;
+    bool fpr_dist = false;
+    size_t seed = std::random_device { } ();
+    size_t batch = 1;
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        auto value = [&](const char* name) -> std::string {
+            if (i + 1 >= argc) {
+                std::cerr << "Error: option " << name << " requires an argument!\n";
+                std::exit(-1);
+            }
+            return argv[++i];
+        };
+        if (a == "-k" || a == "--num-kmers") num_kmers = unsigned(std::strtoul(value("-k").c_str(), nullptr, 10));
+        else if (a == "-q" || a == "--queries") num_queries = unsigned(std::strtoul(value("-q").c_str(), nullptr, 10));
+        else if (a == "-w" || a == "--warmup") num_warmup = unsigned(std::strtoul(value("-w").c_str(), nullptr, 10));
+        else if (a == "-d" || a == "--dist") fpr_dist = true;
+        else if (a == "--seed") seed = std::strtoull(value("--seed").c_str(), nullptr, 10);
+        else if (a == "--batch") batch = std::max<size_t>(1, std::strtoul(value("--batch").c_str(), nullptr, 10));
+        else if (a == "--gpus") cobs::gopt_gpus = unsigned(std::max(1, std::atoi(value("--gpus").c_str())));
+        else if (a == "--device") cobs::gopt_gpu_device = std::atoi(value("--device").c_str());
+        else if (!a.empty() && a[0] == '-') {
+            std::cerr << "Error: unknown option \"" << a << "\".\n";
+            return -1;
+        }
+        else if (in_file.empty()) in_file = a;
+    }
+    if (in_file.empty()) {
+        std::cerr << "Usage: cobs benchmark-fpr [-k num_kmers] [-q queries] [-w warmup] [-d] "
+                     "[--seed s] [--batch n] <in_file>\n";
+        return -1;
+    }
+    // same generator and draw order as the reference: one mt19937 stream, warm-up queries
+    // first (cobs::random_sequence_rng, cobs/util/misc.hpp:31-38)
+    std::mt19937 rng(seed);
+    auto random_sequence = [&](size_t size) {
+        static const char basepairs[4] = { 'A', 'C', 'G', 'T' };
+        std::string r;
+        for (size_t j = 0; j < size; ++j) r += basepairs[rng() % 4];
+        return r;
+    };
+    std::vector<std::string> warmup_queries, queries;
+    for (unsigned i = 0; i < num_warmup; ++i) warmup_queries.push_back(random_sequence(num_kmers + 30));
+    for (unsigned i = 0; i < num_queries; ++i) queries.push_back(random_sequence(num_kmers + 30));
+
+    cobs::ClassicSearch s(std::make_shared<cobs::ClassicIndexMMapSearchFile>(in_file));
+    std::vector<std::vector<cobs::SearchResult> > results;
+    auto run = [&](const std::vector<std::string>& qs, std::map<uint32_t, uint64_t>* counts) {
+        for (size_t b = 0; b < qs.size(); b += batch) {
+            std::vector<std::string> part(qs.begin() + b, qs.begin() + std::min(qs.size(), b + batch));
+            s.search_batch(part, results);
+            if (counts)
+                for (auto& res : results)
+                    for (auto& r : res) (*counts)[r.score]++;
+        }
+    };
+    run(warmup_queries, nullptr);
+    s.timer().reset();
+    std::map<uint32_t, uint64_t> counts;
+    auto t0 = std::chrono::steady_clock::now();
+    run(queries, fpr_dist ? &counts : nullptr);
+    const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+
+    cobs::Timer t = s.timer();
+    std::cout << "RESULT"
+              << " name=benchmark "
+              << " index=" << in_file
+              << " kmer_queries=" << (queries.empty() ? 0 : queries[0].size() - 30)
+              << " queries=" << queries.size()
+              << " warmup=" << warmup_queries.size()
+              << " results=" << (results.empty() ? 0 : results.back().size())
+              << " sse2=off"
+              << " aio=off"
+              << " t_hashes=" << t.get("hashes")
+              << " t_io=" << t.get("io")
+              << " t_and=" << t.get("and rows")
+              << " t_add=" << t.get("add rows")
+              << " t_sort=" << t.get("sort results")
+              << " gpu=on batch=" << batch << " t_wall=" << wall
+              << std::endl;
+    for (const auto& c : counts)
+        std::cout << "RESULT name=benchmark_fpr fpr=" << c.first << " dist=" << c.second << std::endl;
+    return 0;
+}
+
 void usage(const char* prog) {
     std::cout << "(Co)mpact (B)it-Sliced (S)ignature Index for Genome Search -- B200 query path\n\n"
               << "Usage: " << prog << " <subtool> ...\n\n"
               << "Available subtools:\n"
-              << "  query    query an index (classic or compact) on the GPU\n"
-              << "  version  print version\n\n"
+              << "  query          query an index (classic or compact) on the GPU\n"
+              << "  benchmark-fpr  the reference's query micro-benchmark (classic index)\n"
+              << "  version        print version\n\n"
               << "Index construction and the other subtools of the reference are not part of\n"
               << "this build; indices written by the reference are read as they are.\n";
 }
@@ -166,6 +261,7 @@ int main(int argc, char** argv) {
     const std::string tool = argv[1];
     try {
         if (tool == "query") return query(argc - 1, argv + 1);
+        if (tool == "benchmark-fpr") return benchmark_fpr(argc - 1, argv + 1);
         if (tool == "version") {
             std::cout << "COBS B200 query path, C ABI version 1" << std::endl;
             return 0;
