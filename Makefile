@@ -9,7 +9,7 @@ NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused
 CSRC      := cobs_b200/csrc
 LIB       := cobs_b200/lib/libcobsgpu.so
 
-all: $(LIB) host oracle
+all: $(LIB) host oracle build/kernel_unit_tests
 
 $(LIB): $(CSRC)/cobsgpu.cu $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.hpp) include/cobsgpu.h
 	@mkdir -p cobs_b200/lib build
@@ -43,6 +43,13 @@ build/host_tests: cobs_b200/host/tests/host_tests.cpp build/libcobs_b200.so
 build/host_unit_tests: cobs_b200/host/tests/host_unit_tests.cpp build/libcobs_b200.so
 	$(CXX) $(HOST_FLAGS) -o $@ $< -Lbuild -lcobs_b200 -Lcobs_b200/lib -lcobsgpu \
 	    -Wl,-rpath,'$$ORIGIN' -Wl,-rpath,'$$ORIGIN/../cobs_b200/lib'
+
+# host-side unit tests of the __host__ __device__ kernel arithmetic (test infrastructure: links
+# the oracle)
+build/kernel_unit_tests: $(CSRC)/tests/kernel_unit_tests.cu $(wildcard $(CSRC)/*.cuh) oracle
+	@mkdir -p build
+	$(NVCC) $(ARCH) -O2 -std=c++17 --expt-relaxed-constexpr --extended-lambda -Xcompiler -Wno-unknown-pragmas \
+	    -o $@ $< -Loracle -loracle -Xlinker -rpath -Xlinker '$$ORIGIN/../oracle' 2> build/kut.log || (cat build/kut.log; false)
 
 oracle:
 	$(MAKE) -s -C oracle

@@ -198,7 +198,7 @@ __host__ __device__ __forceinline__ bool hash_kmer(const uint8_t* s, uint32_t k_
 //   valid base  <=> bit (c - 'A') of 0x80045 (A, C, G, T)
 //   complement   =  c ^ 0x15 ^ (bit1(c) * 0x11)      (A<->T differ by 0x15, C<->G by 0x04)
 template <int KT, typename Emit>
-__device__ __forceinline__ bool hash_kmer_fixed(const uint8_t (&b)[KT], uint32_t h,
+__host__ __device__ __forceinline__ bool hash_kmer_fixed(const uint8_t (&b)[KT], uint32_t h,
                                                 uint32_t canonicalize, Emit emit) {
     constexpr int NW = (KT + 7) / 8;
     uint64_t w[NW];

@@ -89,7 +89,7 @@ static constexpr int SCORE_PLANES = 8;          // counts up to 255 between flus
     }
 
 // documents of a 32-bit word whose bit-sliced count is >= thr
-__device__ __forceinline__ uint32_t planes_ge(const uint32_t (&pl)[SCORE_PLANES], uint32_t thr) {
+__host__ __device__ __forceinline__ uint32_t planes_ge(const uint32_t (&pl)[SCORE_PLANES], uint32_t thr) {
     if (thr == 0) return 0xFFFFFFFFu;
     if (thr > 255) return 0u;
     uint32_t gt = 0, eq = 0xFFFFFFFFu;
@@ -105,7 +105,7 @@ __device__ __forceinline__ uint32_t planes_ge(const uint32_t (&pl)[SCORE_PLANES]
     return gt | eq;
 }
 
-__device__ __forceinline__ uint32_t planes_count(const uint32_t (&pl)[SCORE_PLANES], uint32_t bit) {
+__host__ __device__ __forceinline__ uint32_t planes_count(const uint32_t (&pl)[SCORE_PLANES], uint32_t bit) {
     uint32_t c = 0;
 #pragma unroll
     for (int i = 0; i < SCORE_PLANES; ++i) c |= ((pl[i] >> bit) & 1u) << i;
@@ -113,7 +113,7 @@ __device__ __forceinline__ uint32_t planes_count(const uint32_t (&pl)[SCORE_PLAN
 }
 
 // counts of documents 4g..4g+3 of a word, one per byte (8x4 bit-matrix transpose by multiply)
-__device__ __forceinline__ uint32_t planes_pack4(const uint32_t (&pl)[SCORE_PLANES], uint32_t g) {
+__host__ __device__ __forceinline__ uint32_t planes_pack4(const uint32_t (&pl)[SCORE_PLANES], uint32_t g) {
     uint32_t out = 0;
 #pragma unroll
     for (int i = 0; i < SCORE_PLANES; ++i) {

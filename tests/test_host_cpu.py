@@ -12,7 +12,7 @@ COBS = os.path.join(ROOT, "build", "cobs")
 
 
 def test_binaries_built():
-    for f in ("cobs", "host_tests", "host_unit_tests", "libcobs_b200.so"):
+    for f in ("cobs", "host_tests", "host_unit_tests", "kernel_unit_tests", "libcobs_b200.so"):
         assert os.path.exists(os.path.join(ROOT, "build", f)), f
 
 
@@ -28,6 +28,15 @@ def test_host_unit_tests_binary():
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert r.returncode == 1
     assert r.stderr.strip() == "query too short, needs to be at least 31 characters long"
+
+
+def test_kernel_arithmetic_unit_tests():
+    """the __host__ __device__ arithmetic of the kernels (XXH64 forms, canonical k-mers, bit-sliced
+    counter helpers, sort keys, procedural fill), executed on the host against the oracle"""
+    r = subprocess.run([os.path.join(ROOT, "build", "kernel_unit_tests")], stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "kernel_unit_tests: ok" in r.stdout
 
 
 def test_usage_and_version():
