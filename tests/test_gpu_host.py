@@ -86,40 +86,3 @@ def test_cli_errors():
     r = run([COBS, "query", "-i", golden_path("all160.cobs_classic"), "ACGT"])
     assert r.returncode == 1 and "query too short" in r.stderr
 
-
-def test_cli_benchmark_fpr_matches_oracle_distribution():
-    """`cobs benchmark-fpr` (src/cobs.cpp:605-730): same mt19937 query stream as the reference
-    (warm-up queries drawn first), threshold 0, all results; the score histogram printed with -d
-    must equal the oracle's over the same queries"""
-    import collections
-    import numpy as np
-    from oracle import oracle
-
-    def mt_queries(seed, n, length):
-        bg = np.random.MT19937()
-        bg._legacy_seeding(seed)
-        raw = bg.random_raw(n * length)
-        b = np.frombuffer(b"ACGT", dtype=np.uint8)[(raw % 4).astype(np.int64)]
-        return [b[i * length:(i + 1) * length].tobytes() for i in range(n)]
-
-    idx = golden_path("random203.cobs_classic")
-    n_warm, n_q, kmers, seed = 3, 25, 70, 7
-    qs = mt_queries(seed, n_warm + n_q, kmers + 30)[n_warm:]
-    o = oracle.Index.load(idx)
-    want = collections.Counter()
-    for q in qs:
-        for _, _, sc in oracle.search(o, q, 0.0, 0):
-            want[sc] += 1
-    for batch in ("1", "8"):
-        r = run([COBS, "benchmark-fpr", "-k", str(kmers), "-q", str(n_q), "-w", str(n_warm),
-                 "--seed", str(seed), "-d", "--batch", batch, idx])
-        assert r.returncode == 0, r.stderr
-        lines = r.stdout.splitlines()
-        assert lines[0].startswith("RESULT name=benchmark ")
-        assert " kmer_queries=70 queries=25 warmup=3 results=203 " in lines[0]
-        got = {}
-        for l in lines[1:]:
-            f = dict(x.split("=") for x in l.split()[1:])
-            assert f["name"] == "benchmark_fpr"
-            got[int(f["fpr"])] = int(f["dist"])
-        assert got == dict(want)
