@@ -53,3 +53,18 @@ def test_cli_benchmark_fpr_matches_oracle_distribution():
             assert f["name"] == "benchmark_fpr"
             got[int(f["fpr"])] = int(f["dist"])
         assert got == dict(want)
+
+
+def test_index_save_round_trips_reference_files(tmp_path, golden):
+    """cobsgpu_index_save writes the reference's formats: loading a file written by the reference
+    and saving it again must reproduce it byte for byte (classic and compact, incl. the compact
+    header's padding rule, cobs/file/compact_index_header.cpp:20-42)"""
+    from cobs_b200 import GpuIndex
+    names = sorted({f for case in golden["cases"] for f in case["files"]})
+    assert any(n.endswith(".cobs_compact") for n in names)
+    for n in names:
+        g = GpuIndex.open_file(golden_path(n))
+        out = str(tmp_path / n)
+        g.save(out)
+        g.close()
+        assert open(out, "rb").read() == open(golden_path(n), "rb").read(), n
