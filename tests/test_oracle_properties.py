@@ -53,7 +53,7 @@ def test_result_list_laws(iq, thr, limit):
     T = len(q) - ix.term_size + 1
     if T * ix.num_hashes <= 1:
         return                                   # the reference's no-sort quirk, tested elsewhere
-    scores = ix.scores(q)
+    scores = [int(x) for x in ix.scores(q)]
     full = oracle.search(ix, q, thr, 0)
     cut = oracle.search(ix, q, thr, limit)
     need = math.ceil(thr * T)
