@@ -268,7 +268,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import cobs_b200
-    from cobs_b200.dist import QuerySplitSearch, ShardedSearch
+    from cobs_b200.dist import GridSearch, QuerySplitSearch, ShardedSearch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -286,17 +286,32 @@ def run_ours(args):
     if args.rows:
         sig = [args.rows] * len(sig)
     split_queries = args.parallelism == "queries" and world > 1
-    index = cobs_b200.GpuIndex.procedural(cfg["kind"], cfg["n_docs"], sig, cfg["h"],
-                                          page_size=cfg["page_size"], fill_seed=FILL_SEED,
-                                          device=local_rank,
-                                          shard_index=0 if (args.emulate_shards or split_queries) else rank,
-                                          shard_count=args.emulate_shards if args.emulate_shards
-                                          else (1 if split_queries else world))
-    index.set_option("max_batch", max(nq, 1))
-    info = index.info
+    grid = args.parallelism == "grid" and world > 1
     rpq = args.results_per_query
-    cls = QuerySplitSearch if split_queries else ShardedSearch
-    sharded = cls(index, rank, world, rpq, overlap=not args.no_overlap)
+
+    def open_index(shard_index, shard_count):
+        ix = cobs_b200.GpuIndex.procedural(cfg["kind"], cfg["n_docs"], sig, cfg["h"],
+                                           page_size=cfg["page_size"], fill_seed=FILL_SEED,
+                                           device=local_rank, shard_index=shard_index,
+                                           shard_count=shard_count)
+        ix.set_option("max_batch", max(nq, 1))
+        return ix
+
+    if grid:
+        # documents x queries: --doc-shards D ranks share one copy of the index, world / D copies
+        sharded = GridSearch(open_index, rank, world, args.doc_shards, rpq,
+                             overlap=not args.no_overlap)
+        index = sharded.index
+    else:
+        if args.emulate_shards:
+            index = open_index(0, args.emulate_shards)
+        elif split_queries:
+            index = open_index(0, 1)
+        else:
+            index = open_index(rank, world)
+        cls = QuerySplitSearch if split_queries else ShardedSearch
+        sharded = cls(index, rank, world, rpq, overlap=not args.no_overlap)
+    info = index.info
 
     # bytes per k-mer of the WHOLE index (h * ceil(N/8), unpadded reference layout)
     if cfg["kind"] == 0:
@@ -355,7 +370,7 @@ def run_ours(args):
     launches = tm["kernel_launches"] + (args.steps if world > 1 else 0)
     index.set_option("timing", 0)
     index.set_option("inputs_ready", 0)     # the e2e leg uploads its queries itself
-    n_results = int((last[0].cpu().numpy().view(np.uint32).reshape(-1) % 0xFFFFFFFE).sum())
+    n_results = int((last[-2].cpu().numpy().view(np.uint32).reshape(-1) % 0xFFFFFFFE).sum())
 
     # ---- leg 2: end to end from host buffers through the public API ("e2e") ----
     h2d = int(pinned[0].numel() + off.nbytes)
@@ -416,6 +431,9 @@ def run_ours(args):
     if split_queries:
         per = (nq + world - 1) // world
         algo_bytes_per_launch = info.bytes_per_kmer * per * T
+    if grid:
+        lo, hi = sharded.slice_of(nq)
+        algo_bytes_per_launch = info.bytes_per_kmer * (hi - lo) * T
     achieved = algo_bytes_per_launch / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else 0.0
 
     if rank == 0:
@@ -436,6 +454,9 @@ def run_ours(args):
                        "parallelism": ("single GPU" if world == 1 else
                                        "index replicated x%d, queries split, NCCL all-gather of "
                                        "the result blocks" % world if split_queries else
+                                       "%d document shards x %d query groups, NCCL all-gather + "
+                                       "merge inside each group" % (args.doc_shards, world // args.doc_shards)
+                                       if grid else
                                        "document-axis shards x%d, NCCL all-gather of per-rank "
                                        "result blocks + merge" % world),
                        "queries_per_step": nq, "kmers_per_query": T,
@@ -477,9 +498,11 @@ def main():
     ap.add_argument("--ref-queries", type=int, default=400,
                     help="queries per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--parallelism", default="docs", choices=["docs", "queries"],
-                    help="N > 1: shard the document axis (default, BASELINE.json's north_star) or "
-                         "replicate the index and split every query batch")
+    ap.add_argument("--parallelism", default="docs", choices=["docs", "queries", "grid"],
+                    help="N > 1: shard the document axis (default, BASELINE.json's north_star), "
+                         "replicate the index and split every query batch, or both (grid: "
+                         "--doc-shards ranks share one copy of the index)")
+    ap.add_argument("--doc-shards", type=int, default=2, help="document shards per copy (grid)")
     ap.add_argument("--emulate-shards", type=int, default=0,
                     help="debug: hold shard 0 of this many document shards on one GPU")
     ap.add_argument("--no-overlap", action="store_true",

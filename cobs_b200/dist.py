@@ -247,6 +247,72 @@ class QuerySplitSearch(ShardedSearch):
         return self.rpq if num_results == 0 else min(num_results, self.rpq)
 
 
+class GridSearch:
+    """Documents AND queries sharded: world = doc_shards x query_groups.  Rank r belongs to query
+    group r // doc_shards and holds document shard r % doc_shards; every query group searches its
+    contiguous slice of each batch over its own complete copy of the index (spread over
+    doc_shards GPUs) and exchanges only inside the group.  With doc_shards == world this is
+    ShardedSearch, with doc_shards == 1 QuerySplitSearch without the final gather.  It keeps the
+    row slices per GPU longer than a pure document split when the index is small enough to be
+    held query_groups times."""
+
+    def __init__(self, index_factory, rank, world, doc_shards, results_per_query=64, overlap=False,
+                 depth=4):
+        """index_factory(shard_index, shard_count) -> GpuIndex for this rank's document shard"""
+        if world % doc_shards != 0:
+            raise ValueError("world size must be a multiple of doc_shards")
+        self.rank, self.world, self.doc_shards = rank, world, doc_shards
+        self.query_groups = world // doc_shards
+        self.group_index = rank // doc_shards
+        self.shard_index = rank % doc_shards
+        # every rank has to take part in the creation of every subgroup
+        self.group = None
+        for g in range(self.query_groups):
+            ranks = list(range(g * doc_shards, (g + 1) * doc_shards))
+            pg = dist.new_group(ranks) if (world > 1 and doc_shards > 1) else None
+            if g == self.group_index:
+                self.group = pg
+        self.index = index_factory(self.shard_index, doc_shards)
+        self.inner = self._make_inner(results_per_query, overlap, depth)
+
+    def _make_inner(self, rpq, overlap, depth):
+        return ShardedSearch(self.index, self.shard_index, self.doc_shards, rpq, group=self.group,
+                             overlap=overlap, depth=depth)
+
+    def slice_of(self, nq):
+        """[lo, hi) of a batch of nq queries handled by this rank's query group"""
+        per = (nq + self.query_groups - 1) // self.query_groups
+        lo = min(self.group_index * per, nq)
+        return lo, min(lo + per, nq)
+
+    def search_device(self, d_queries, off, threshold, num_results):
+        """searches this group's slice of the batch; returns (lo, hi, counts, keys) with the
+        merged results of queries [lo, hi) as ShardedSearch.search_device returns them"""
+        lo, hi = self.slice_of(len(off) - 1)
+        if hi == lo:      # more query groups than queries: nothing to do for this whole group
+            return lo, hi, None, None
+        counts, keys = self.inner.search_device(d_queries, off[lo:hi + 1], threshold, num_results)
+        return lo, hi, counts, keys
+
+    def join(self):
+        self.inner.join()
+
+    # streaming end-to-end use, see ShardedSearch.submit_host / collect
+    @property
+    def depth(self):
+        return self.inner.depth
+
+    def submit_host(self, h_queries, off, threshold, num_results):
+        lo, hi = self.slice_of(len(off) - 1)
+        return self.inner.submit_host(h_queries, off[lo:hi + 1], threshold, num_results)
+
+    def collect(self, ticket):
+        return self.inner.collect(ticket)
+
+    def search_host(self, h_queries, off, threshold, num_results):
+        return self.collect(self.submit_host(h_queries, off, threshold, num_results))
+
+
 def shard_bounds_classic(row_size, shard_count):
     """column-byte ranges of a classic index cut at multiples of 128 documents -- must match
     build_layout() in cobs_b200/csrc/cobsgpu.cu"""

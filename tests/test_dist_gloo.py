@@ -191,3 +191,71 @@ def test_world2_gloo_shard_merge():
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert dict(ret) == {0: True, 1: True}
+
+
+def _grid_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cobs_b200.dist import GridSearch, ShardedSearch, shard_bounds_classic, OVERFLOW
+    from oracle import oracle
+
+    o = oracle.Index.procedural(oracle.KIND_CLASSIC, N_DOCS, SIG, H, fill_seed=SEED,
+                                materialize=True)
+    row = (N_DOCS + 7) // 8
+
+    class CpuShard(ShardedSearch):
+        def _local_search(self, d_queries, off, threshold, num_results, counts, keys):
+            b0, b1 = shard_bounds_classic(row, self.world)[self.rank]
+            blob = bytes(d_queries.numpy())
+            for i in range(len(off) - 1):
+                q = blob[int(off[i]):int(off[i + 1])]
+                sc = o.scores(q, 8 * b0, 8 * b1)
+                thr = int(np.ceil(threshold * (len(q) - 30)))
+                docs = [d for d in range(8 * b0, min(8 * b1, N_DOCS)) if sc[d - 8 * b0] >= thr]
+                docs.sort(key=lambda d: (-int(sc[d - 8 * b0]), d))
+                docs = (docs[:num_results] if num_results else docs)[:self.rpq]
+                counts[i] = len(docs)
+                for j, d in enumerate(docs):
+                    keys[i, j] = int(np.int64(_key(int(sc[d - 8 * b0]), d).view(np.int64)))
+
+        def _merge(self, all_counts, all_keys, num_results, out_counts, out_keys):
+            c = all_counts.numpy().view(np.uint32)
+            k = all_keys.numpy().view(np.uint64)
+            for i in range(c.shape[1]):
+                m = np.sort(np.concatenate([k[r, i, :c[r, i]] for r in range(c.shape[0])]))
+                m = (m[:num_results] if num_results else m)[:out_keys.shape[1]]
+                out_counts[i] = len(m)
+                out_keys[i, :len(m)] = torch.from_numpy(m.view(np.int64))
+
+    class CpuGrid(GridSearch):
+        def _make_inner(self, rpq, overlap, depth):
+            return CpuShard(None, self.shard_index, self.doc_shards, rpq, group=self.group)
+
+    g = CpuGrid(lambda si, sc: None, rank, world, doc_shards=2, results_per_query=64)
+    ok = (g.query_groups == 2 and g.group_index == rank // 2 and g.shard_index == rank % 2)
+    queries = [oracle.random_query(i, 100) for i in range(9)]       # 9 queries: slices 5 + 4
+    blob = torch.frombuffer(bytearray(b"".join(queries)), dtype=torch.uint8)
+    off = np.arange(len(queries) + 1, dtype=np.uint64) * 100
+    for thr, k in ((0.12, 6), (0.3, 0)):
+        lo, hi, counts, keys = g.search_device(blob, off, thr, k)
+        ok &= (lo, hi) == ((0, 5) if rank < 2 else (5, 9))
+        c = counts.numpy().view(np.uint32)
+        kk = keys.numpy().view(np.uint64)
+        for i, q in enumerate(queries[lo:hi]):
+            got = [(0, int(x & np.uint64(0xFFFFFFFF)),
+                    int(~(x >> np.uint64(32)) & np.uint64(0xFFFFFFFF))) for x in kk[i, :c[i]]]
+            ok &= got == oracle.search(o, q, thr, k)
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_world4_gloo_grid_docs_x_queries():
+    """2 document shards x 2 query groups on 4 gloo ranks: subgroup exchange only"""
+    world = 4
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_grid_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True, 2: True, 3: True}
