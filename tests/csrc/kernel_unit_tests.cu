@@ -10,10 +10,10 @@
 #include <string>
 #include <vector>
 
-#include "../common.cuh"
-#include "../hash.cuh"
-#include "../score.cuh"
-#include "../../../oracle/cobs_oracle.h"
+#include "../../cobs_b200/csrc/common.cuh"
+#include "../../cobs_b200/csrc/hash.cuh"
+#include "../../cobs_b200/csrc/score.cuh"
+#include "../../oracle/cobs_oracle.h"
 
 using namespace cobsgpu;
 
