@@ -294,7 +294,8 @@ class Search:
         # `limit` kept documents in column order.  Those queries need the untruncated list.
         quirk = [qi for qi in range(nq) if qlens[qi] >= max(ix.term_size for ix in self.indices)
                  and hashes_of(qi) <= 1]
-        normal = [qi for qi in range(nq) if qi not in set(quirk)]
+        quirk_set = set(quirk)
+        normal = [qi for qi in range(nq) if qi not in quirk_set]
         per_index = [dict() for _ in self.indices]
         for f, ix in enumerate(self.indices):
             # per-index lists, each already ordered (score desc, doc asc) and cut at
