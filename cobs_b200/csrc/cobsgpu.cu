@@ -603,6 +603,7 @@ void prepare_batch(cobsgpu_index* ix, const char* queries, bool dev_queries,
                    cudaStream_t st) {
     const uint32_t nq = q1 - q0;
     const uint32_t k = ix->term_size;
+    if (std::isnan(threshold)) throw Err{ COBSGPU_ERR_INVALID_ARG, "threshold is NaN" };
     // Streaming workloads (fixed-length reads) present the same offsets batch after batch:
     // the derived geometry is cached and, when the device copy of this buffer set is current,
     // only the flag words are re-armed on the device instead of a rebuild + upload.
