@@ -86,6 +86,11 @@ private:
         return ok;
     }
     void names(uint32_t n) {
+        // every name ends with '\n': a count beyond the remaining bytes is a corrupt header
+        if (bad_ || n > map_size - pos_) {
+            bad_ = true;
+            return;
+        }
         doc_names.resize(n);
         for (uint32_t i = 0; i < n && !bad_; ++i) {
             const void* nl = std::memchr(map + pos_, '\n', map_size - pos_);
@@ -118,7 +123,7 @@ private:
             page_size = (static_cast<uint64_t>(n_docs) + 7) / 8;
             signature_sizes = { sig };
             data_pos = pos_;
-            if (pos_ + sig * page_size > map_size) return "index file truncated";
+            if (page_size != 0 && sig > (map_size - pos_) / page_size) return "index file truncated";
             page_data = { map + pos_ };
             return "";
         }
@@ -133,6 +138,7 @@ private:
         n_docs = get<uint32_t>();
         page_size = get<uint64_t>();
         if (bad_ || n_params == 0 || page_size == 0) return "input filestream broken";
+        if (n_params > (map_size - pos_) / 16) return "input filestream broken";
         signature_sizes.resize(n_params);
         for (uint32_t i = 0; i < n_params; ++i) {
             signature_sizes[i] = get<uint64_t>();
@@ -146,17 +152,21 @@ private:
         if (bad_) return "input filestream broken";
         // zero padding so that the matrix starts page_size-aligned
         // (compact_index_header.cpp:20-22, 62-63)
-        pos_ += (page_size - ((pos_ + 13) % page_size)) % page_size;
+        {
+            const uint64_t pad = (page_size - ((pos_ + 13) % page_size)) % page_size;
+            if (pad > map_size - pos_) return "input filestream broken";
+            pos_ += pad;
+        }
         if (!magic("COMPACT_INDEX")) return "invalid file type";
         kind = 1;
         data_pos = pos_;
         page_data.resize(n_params);
         size_t p = pos_;
         for (uint32_t i = 0; i < n_params; ++i) {
+            if (signature_sizes[i] > (map_size - p) / page_size) return "index file truncated";
             page_data[i] = map + p;
             p += signature_sizes[i] * page_size;
         }
-        if (p > map_size) return "index file truncated";
         return "";
     }
 };
