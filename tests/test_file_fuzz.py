@@ -55,3 +55,22 @@ def test_corrupt_index_files_are_rejected_cleanly(tmp_path):
                        stderr=subprocess.PIPE, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr[-2000:]
     assert "fuzzed 1230" in r.stdout
+
+
+def test_valid_files_pass_the_parser():
+    """every golden file written by the reference gets through header parsing and the size
+    checks; without a GPU the call then stops at the device (ERR_CUDA), never at the parser"""
+    import ctypes as C
+    import glob
+
+    import pytest
+    import cobs_b200
+    from cobs_b200 import _lib
+    L = cobs_b200.lib()
+    if L.cobsgpu_device_count() > 0:
+        pytest.skip("GPU present: the loader itself is covered by the gpu tests")
+    files = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.cobs_*")))
+    assert len(files) >= 14
+    for p in files:
+        h = C.c_void_p()
+        assert L.cobsgpu_index_open_file(p.encode(), 0, 0, 1, C.byref(h)) == _lib.ERR_CUDA, p
