@@ -131,6 +131,9 @@ SYMBOLS = {
     "cobsgpu_scores": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "cobsgpu_search_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                        C.c_double, C.c_uint64, C.POINTER(Result)]),
+    "cobsgpu_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_double,
+                                 C.c_uint64, C.POINTER(C.c_uint64)]),
+    "cobsgpu_collect": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(Result)]),
     "cobsgpu_search_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                               C.c_double, C.c_uint64, C.c_uint32, C.c_void_p,
                                               C.c_void_p, C.c_void_p]),

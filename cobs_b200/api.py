@@ -209,6 +209,25 @@ class GpuIndex:
         bp = blob.ctypes.data if isinstance(blob, np.ndarray) else blob
         _lib.check(_lib.lib().cobsgpu_search_batch(self._h, bp, off.ctypes.data, nq,
                                                    threshold, num_results, C.byref(r)))
+        return self._unpack(r, nq, raw)
+
+    def submit(self, blob, off, threshold=0.0, num_results=0):
+        """asynchronous half of search_packed: enqueue one batch (at most `max_batch` queries),
+        returns a ticket for collect().  Up to 4 tickets may be outstanding; `blob` and `off`
+        must stay alive until the ticket is collected."""
+        t = C.c_uint64()
+        bp = blob.ctypes.data if isinstance(blob, np.ndarray) else blob
+        _lib.check(_lib.lib().cobsgpu_submit(self._h, bp, off.ctypes.data, len(off) - 1,
+                                             threshold, num_results, C.byref(t)))
+        return (t.value, len(off) - 1, blob, off)
+
+    def collect(self, ticket, raw=False):
+        r = _lib.Result()
+        _lib.check(_lib.lib().cobsgpu_collect(self._h, ticket[0], C.byref(r)))
+        return self._unpack(r, ticket[1], raw)
+
+    @staticmethod
+    def _unpack(r, nq, raw):
         roff = np.ctypeslib.as_array(r.offsets, shape=(nq + 1,)).copy()
         total = int(roff[nq])
         if total:

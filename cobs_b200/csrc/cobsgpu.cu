@@ -104,6 +104,19 @@ struct PinBuf {
         CK(cudaMallocHost(&p, n));
         cap = n;
     }
+    // grows the buffer, preserving its first `keep` bytes
+    void ensure_keep(size_t n, size_t keep) {
+        if (n <= cap) return;
+        void* q = nullptr;
+        n = round_up<size_t>(n + n / 4, 256);
+        CK(cudaMallocHost(&q, n));
+        if (p) {
+            std::memcpy(q, p, std::min(keep, cap));
+            cudaFreeHost(p);
+        }
+        p = q;
+        cap = n;
+    }
     template <typename T>
     T* as() const {
         return static_cast<T*>(p);
@@ -124,6 +137,71 @@ struct LocalPage {
     uint32_t n_real;        // real documents among the 8*row_bytes columns held
     uint32_t dense_off;     // first column in the shard-local dense layout
     uint8_t* d_base;
+};
+
+// Everything one batch needs from upload to collected result.  The handle rotates through a
+// small ring of these so that the upload + K1 of batch i+1 and the download of batch i-1 overlap
+// the score kernel of batch i.
+struct Slot {
+    // host geometry of the batch
+    std::vector<uint64_t> qoff;          // [nq+1] byte offsets inside the batch blob
+    std::vector<uint32_t> koff, thr;     // [nq+1] k-mer prefix, [nq] ceil(threshold * T_q)
+    uint32_t nq = 0, total_kmers = 0, uniform_T = 0, max_T = 0;
+    std::vector<uint64_t> geo_offsets;   // the caller's offsets this geometry was derived from
+    double geo_threshold = 0;
+    bool geo_valid = false;
+    bool meta_resident = false;          // d_meta holds this geometry: only re-arm the flags
+    void* meta_ptr = nullptr;
+    // device: d_meta = [flags 2 x int | bad nq x u32 | qoff | koff | thr] in one block,
+    // d_out = [flags 2 x int | offsets (nq+1) x u64 | cand_count nq x u32 | keys ...]
+    DevBuf d_queries, d_meta, d_hashes, d_cand, d_scratch, d_res_count, d_out, d_qlist, d_dense;
+    size_t meta_qoff = 0, meta_koff = 0, meta_thr = 0, meta_bad = 0;
+    size_t out_off = 0, out_cc = 0, out_keys = 0;
+    const char* dev_queries = nullptr;
+    PinBuf h_meta, h_out;
+    cudaEvent_t ev_meta = nullptr, ev_in = nullptr, ev_main = nullptr, ev_out = nullptr;
+    // the submitted batch
+    bool busy = false;
+    uint64_t ticket = 0;
+    uint32_t q0 = 0;                     // first query of the batch inside the caller's call
+    double threshold = 0;
+    uint64_t limit = 0;
+    int mode = 0;                        // MODE_CAND / MODE_TOPK, or -1: exhaustive at collect
+    bool lng = false;
+    uint32_t cap = 0;
+    uint64_t spec_keys = 0;              // keys copied back speculatively with the header
+    std::vector<uint32_t> main_ids;      // queries of the main pass when not all of them
+    std::vector<uint32_t> huge_ids;      // queries of more than 65 535 k-mers
+    // collected result (valid until the slot is submitted again)
+    std::vector<uint64_t> r_off;
+    std::vector<uint32_t> r_doc, r_score;
+
+    int* d_flags() const { return d_meta.as<int>(); }
+    uint32_t* d_bad() const { return reinterpret_cast<uint32_t*>(d_meta.as<char>() + meta_bad); }
+    uint64_t* d_qoff() const { return reinterpret_cast<uint64_t*>(d_meta.as<char>() + meta_qoff); }
+    uint32_t* d_koff() const { return reinterpret_cast<uint32_t*>(d_meta.as<char>() + meta_koff); }
+    uint32_t* d_thr() const { return reinterpret_cast<uint32_t*>(d_meta.as<char>() + meta_thr); }
+    // result header / keys inside d_out for n query slots
+    void layout_out(uint32_t n) {
+        out_off = 8;
+        out_cc = out_off + (static_cast<size_t>(n) + 1) * 8;
+        out_keys = round_up<size_t>(out_cc + static_cast<size_t>(n) * 4, 8);
+    }
+    int* o_flags() const { return d_out.as<int>(); }
+    uint64_t* o_off() const { return reinterpret_cast<uint64_t*>(d_out.as<char>() + out_off); }
+    uint32_t* o_cc() const { return reinterpret_cast<uint32_t*>(d_out.as<char>() + out_cc); }
+    uint64_t* o_keys() const { return reinterpret_cast<uint64_t*>(d_out.as<char>() + out_keys); }
+    cudaEvent_t& ev(cudaEvent_t& e) {
+        if (!e) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        return e;
+    }
+    void release() {
+        for (cudaEvent_t* e : { &ev_meta, &ev_in, &ev_main, &ev_out })
+            if (*e) {
+                cudaEventDestroy(*e);
+                *e = nullptr;
+            }
+    }
 };
 
 enum Phase { PH_H2D = 0, PH_HASH, PH_SCORE, PH_SELECT, PH_D2H };
@@ -152,7 +230,10 @@ struct cobsgpu_index {
     uint32_t shard_doc_begin = 0, shard_doc_end = 0;
     uint64_t bytes_per_kmer = 0;
     uint32_t* d_seg = nullptr;    // [3][n_local_pages]: dense_off, n_real, doc_base
-    unsigned long long* d_work = nullptr;   // score kernel work counters (zero between launches)
+    // score kernel work counters: WORK_RING pairs {next item, CTAs finished}, zero between launches
+    static constexpr uint32_t WORK_RING = 16;
+    unsigned long long* d_work = nullptr;
+    uint32_t work_slot = 0;
 
     // device properties
     int sm_count = 0;
@@ -164,52 +245,26 @@ struct cobsgpu_index {
     uint64_t workspace_bytes = 1024ull << 20;
     bool timing = false;
 
-    // execution state
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    DevBuf d_queries, d_meta_[2], d_hashes_[2], d_qlist;
-    // two sets of {metadata, hashes}: with "prefetch" on, the device-resident path runs the
-    // upload + K1 of call i+1 on pre_stream while K2 of call i still reads set i
-    int cur = 0;
-    DevBuf& meta() { return d_meta_[cur]; }
-    DevBuf& hashes() { return d_hashes_[cur]; }
+    // execution state: three streams so that consecutive batches overlap -- s_in uploads the
+    // queries + metadata and runs K1, `stream` (main) runs K2 + K3, s_out copies results back
+    cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
+    static constexpr int N_SLOTS = 4;     // batches in flight (submit/collect tickets)
+    Slot slots[N_SLOTS];
+    Slot aux;                             // workspace of the exhaustive passes / cobsgpu_scores
+    int next_slot = 0;
+    uint64_t ticket_counter = 0;
     bool prefetch = false, inputs_ready = false;
-    cudaStream_t pre_stream = nullptr;
-    cudaEvent_t ev_in = nullptr, ev_k1[2] = { nullptr, nullptr }, ev_k2[2] = { nullptr, nullptr };
-    bool ev_k2_valid[2] = { false, false };
-    // per-batch metadata travels as ONE block: [flags 2 x int | qoff | koff | thr], staged in a
-    // ring of pinned buffers so that the upload is truly asynchronous
-    static constexpr int META_RING = 4;
-    PinBuf h_meta[META_RING];
-    cudaEvent_t meta_ev[META_RING] = { nullptr, nullptr, nullptr, nullptr };
-    int meta_slot = 0;
-    size_t meta_qoff = 0, meta_koff = 0, meta_thr = 0, meta_bad = 0;   // byte offsets inside d_meta
-    int* d_flags() const { return d_meta_[cur].as<int>(); }
-    uint64_t* d_qoff() const { return reinterpret_cast<uint64_t*>(d_meta_[cur].as<char>() + meta_qoff); }
-    uint32_t* d_koff() const { return reinterpret_cast<uint32_t*>(d_meta_[cur].as<char>() + meta_koff); }
-    uint32_t* d_thr() const { return reinterpret_cast<uint32_t*>(d_meta_[cur].as<char>() + meta_thr); }
-    uint32_t* d_bad() const { return reinterpret_cast<uint32_t*>(d_meta_[cur].as<char>() + meta_bad); }
+    cudaEvent_t ev_caller = nullptr;      // device path: caller's stream -> s_in ordering
     // cached launch configuration of the score kernel per mode
     struct ScoreCfg {
         bool valid = false;
         uint32_t n_stages = 0;
         size_t smem = 0;
         int occupancy = 0;
-    } score_cfg[3];
-    DevBuf d_cand, d_scratch, d_cand_count, d_res_count, d_offsets, d_out_doc, d_out_score, d_dense;
-    PinBuf h_off, h_doc, h_score, h_counts, h_dense;
-    // current batch (host copies) and the cache of its geometry
-    std::vector<uint64_t> b_qoff;
-    std::vector<uint32_t> b_koff, b_thr;
-    uint32_t b_nq = 0, b_total_kmers = 0, b_uniform_T = 0;
-    std::vector<uint64_t> geo_offsets;      // the caller's offsets the cached geometry belongs to
-    double geo_threshold = 0;
-    uint64_t geo_version = 0, geo_counter = 0;
-    uint64_t meta_version[2] = { 0, 0 };    // geometry version resident in d_meta_[set]
-    void* meta_ptr[2] = { nullptr, nullptr };
-    const char* b_dev_queries = nullptr;
+    } score_cfg[SCORE_MODES][2];   // [mode][8 or 16 bit-planes]
+    uint32_t warps_per_query = 0;         // consumer warps that see one query (TOPK candidate bound)
 
-    // results of the last search_batch call
+    // results of the last cobsgpu_search_batch call
     std::vector<uint64_t> r_off;
     std::vector<uint32_t> r_doc, r_score;
 
@@ -224,24 +279,22 @@ struct cobsgpu_index {
 
     ~cobsgpu_index() {
         cudaSetDevice(device);
+        for (cudaStream_t st : { s_in, stream, s_out })
+            if (st) cudaStreamSynchronize(st);
         for (auto& e : pending) {
             cudaEventDestroy(e.a);
             cudaEventDestroy(e.b);
         }
         for (auto e : ev_pool) cudaEventDestroy(e);
-        for (auto e : meta_ev)
-            if (e) cudaEventDestroy(e);
+        for (Slot& sl : slots) sl.release();
+        aux.release();
+        if (ev_caller) cudaEventDestroy(ev_caller);
         if (d_arena) cudaFree(d_arena);
         if (d_tiles) cudaFree(d_tiles);
         if (d_seg) cudaFree(d_seg);
         if (d_work) cudaFree(d_work);
-        if (pre_stream) {
-            cudaStreamSynchronize(pre_stream);
-            cudaStreamDestroy(pre_stream);
-        }
-        for (cudaEvent_t e : { ev_in, ev_k1[0], ev_k1[1], ev_k2[0], ev_k2[1] })
-            if (e) cudaEventDestroy(e);
-        if (own_stream && stream) cudaStreamDestroy(stream);
+        for (cudaStream_t st : { s_in, stream, s_out })
+            if (st) cudaStreamDestroy(st);
     }
 };
 
@@ -414,6 +467,8 @@ void build_tiles(cobsgpu_index* ix) {
             ix->tiles.push_back(t);
         }
     }
+    ix->warps_per_query = 0;
+    for (const TileDesc& t : ix->tiles) ix->warps_per_query += div_ceil<uint32_t>(t.bytes, 512);
     if (!ix->tiles.empty()) {
         CK(cudaMalloc(&ix->d_tiles, ix->tiles.size() * sizeof(TileDesc)));
         CK(cudaMemcpy(ix->d_tiles, ix->tiles.data(), ix->tiles.size() * sizeof(TileDesc),
@@ -465,8 +520,8 @@ void open_common(cobsgpu_index* ix, const std::vector<uint64_t>& sig,
     check_device(ix->device);
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, ix->device));
-    if (prop.major < 9)
-        throw Err{ COBSGPU_ERR_CUDA, "device lacks bulk-copy/mbarrier support (need sm_100)" };
+    if (prop.major < 10)   // the library is built for sm_100a only (Makefile)
+        throw Err{ COBSGPU_ERR_CUDA, "unsupported device: libcobsgpu is built for sm_100 (B200) only" };
     ix->sm_count = prop.multiProcessorCount;
     ix->smem_optin = prop.sharedMemPerBlockOptin;
     if (ix->num_hashes == 0 || ix->num_hashes > 32)
@@ -482,8 +537,15 @@ void open_common(cobsgpu_index* ix, const std::vector<uint64_t>& sig,
 
     ix->signature_sizes = sig;
     build_layout(ix, sig);
-    CK(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
-    ix->own_stream = true;
+    {
+        // uploads + K1 and the result copies get the higher priority: they are short and the
+        // next score kernel waits for them
+        int lo_p = 0, hi_p = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+        CK(cudaStreamCreateWithPriority(&ix->stream, cudaStreamNonBlocking, lo_p));
+        CK(cudaStreamCreateWithPriority(&ix->s_in, cudaStreamNonBlocking, hi_p));
+        CK(cudaStreamCreateWithPriority(&ix->s_out, cudaStreamNonBlocking, hi_p));
+    }
     if (ix->hbm_bytes) {
         CK(cudaMalloc(reinterpret_cast<void**>(&ix->d_arena), ix->hbm_bytes));
         uint64_t off = 0;
@@ -518,8 +580,8 @@ void open_common(cobsgpu_index* ix, const std::vector<uint64_t>& sig,
         CK(cudaStreamSynchronize(ix->stream));
     }
     build_tiles(ix);
-    CK(cudaMalloc(reinterpret_cast<void**>(&ix->d_work), 16));
-    CK(cudaMemset(ix->d_work, 0, 16));
+    CK(cudaMalloc(reinterpret_cast<void**>(&ix->d_work), 16 * cobsgpu_index::WORK_RING));
+    CK(cudaMemset(ix->d_work, 0, 16 * cobsgpu_index::WORK_RING));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -527,31 +589,35 @@ void open_common(cobsgpu_index* ix, const std::vector<uint64_t>& sig,
 
 using ScoreFn = void (*)(const ScoreParams);
 
-template <int MODE>
+template <int MODE, int NP>
 ScoreFn pick_h(uint32_t h) {
     switch (h) {
-    case 1: return score_kernel<1, MODE>;
-    case 2: return score_kernel<2, MODE>;
-    case 3: return score_kernel<3, MODE>;
-    case 4: return score_kernel<4, MODE>;
-    default: return score_kernel<0, MODE>;
+    case 1: return score_kernel<1, MODE, NP>;
+    case 2: return score_kernel<2, MODE, NP>;
+    case 3: return score_kernel<3, MODE, NP>;
+    case 4: return score_kernel<4, MODE, NP>;
+    default: return score_kernel<0, MODE, NP>;
     }
 }
 
-ScoreFn pick_score(uint32_t h, int mode) {
+// lng = 16 bit-planes (queries of up to 65 535 k-mers); the dense modes exist for 8 planes
+// only (DENSE32 flushes into u32 scores before the planes overflow, whatever the query length)
+ScoreFn pick_score(uint32_t h, int mode, bool lng) {
     switch (mode) {
-    case MODE_CAND: return pick_h<MODE_CAND>(h);
-    case MODE_DENSE8: return pick_h<MODE_DENSE8>(h);
-    default: return pick_h<MODE_DENSE32>(h);
+    case MODE_CAND: return lng ? pick_h<MODE_CAND, 16>(h) : pick_h<MODE_CAND, 8>(h);
+    case MODE_TOPK: return lng ? pick_h<MODE_TOPK, 16>(h) : pick_h<MODE_TOPK, 8>(h);
+    case MODE_DENSE8: return pick_h<MODE_DENSE8, 8>(h);
+    default: return pick_h<MODE_DENSE32, 8>(h);
     }
 }
 
-void launch_score(cobsgpu_index* ix, ScoreParams sp, int mode, cudaStream_t st) {
+void launch_score(cobsgpu_index* ix, ScoreParams sp, int mode, bool lng, cudaStream_t st) {
     if (sp.nq_items == 0 || sp.n_tiles == 0) return;
     const uint32_t h = ix->num_hashes;
-    ScoreFn fn = pick_score(h, mode);
+    ScoreFn fn = pick_score(h, mode, lng);
     const int threads = static_cast<int>((ix->ncw + 1) * 32);
-    cobsgpu_index::ScoreCfg& cfg = ix->score_cfg[mode];
+    if (mode == MODE_DENSE8 || mode == MODE_DENSE32) lng = false;
+    cobsgpu_index::ScoreCfg& cfg = ix->score_cfg[mode][lng ? 1 : 0];
     if (!cfg.valid) {
         const uint32_t W = ix->ncw * 512;
         const uint32_t stage = h * W;
@@ -574,13 +640,20 @@ void launch_score(cobsgpu_index* ix, ScoreParams sp, int mode, cudaStream_t st) 
         if (e_st) ns = std::max<uint32_t>(1, std::min<uint32_t>(ns, static_cast<uint32_t>(std::atoi(e_st))));
         cfg.n_stages = ns;
         cfg.smem = score_smem_header(ns) + static_cast<size_t>(ns) * stage;
+        // The attribute belongs to the kernel function (per device), not to this handle: every
+        // handle sets the same device-wide maximum, so handles with different tile widths (or
+        // host threads racing on one device) can never lower each other's limit.
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                static_cast<int>(cfg.smem)));
+                                static_cast<int>(ix->smem_optin)));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.occupancy, fn, threads, cfg.smem));
         if (cfg.occupancy < 1) throw Err{ COBSGPU_ERR_CUDA, "score kernel does not fit on an SM" };
         cfg.valid = true;
     }
     sp.n_stages = cfg.n_stages;
+    // work counters: one pair per launch out of a ring, so that score kernels of this handle
+    // running concurrently on different streams never share a pair (the last CTA of a launch
+    // re-arms its own pair)
+    sp.work = ix->d_work + 2 * (ix->work_slot++ % cobsgpu_index::WORK_RING);
     const uint64_t items = static_cast<uint64_t>(sp.nq_items) * sp.n_tiles;
     const uint32_t grid = static_cast<uint32_t>(
         std::min<uint64_t>(items, static_cast<uint64_t>(cfg.occupancy) * ix->sm_count));
@@ -594,30 +667,36 @@ void launch_score(cobsgpu_index* ix, ScoreParams sp, int mode, cudaStream_t st) 
 // ---------------------------------------------------------------------------------------
 // batch preparation: host geometry, uploads, K1
 
-// d_meta starts with two flags: [0] first query with an invalid base, [1] first query
-// overflowing its candidate slots (both FLAG_CLEAR when clear)
+// d_meta starts with two flags: [0] first query with an invalid base ([1] unused), FLAG_CLEAR
+// when clear; the per-query `bad` words behind them are armed with the same byte pattern
 static constexpr int FLAG_CLEAR = 0x7F7F7F7F;
-// queries [q0, q1) of the caller's batch; `queries` is a host pointer unless dev_queries
-void prepare_batch(cobsgpu_index* ix, const char* queries, bool dev_queries,
+static constexpr uint32_t MAX_T_SHORT = 255;      // 8 bit-planes
+static constexpr uint32_t MAX_T_LONG = 65535;     // 16 bit-planes
+static constexpr uint32_t TOPK_MAX_K = 1024;      // largest -l served by the per-warp top-k epilogue
+
+// Fills slot `sl` with queries [q0, q1) of the caller's batch: host geometry, upload of the
+// queries (unless they already live on the device) and of the metadata block, K1 -- all on `st`.
+void prepare_batch(cobsgpu_index* ix, Slot& sl, const char* queries, bool dev_queries,
                    const uint64_t* offsets, uint32_t q0, uint32_t q1, double threshold,
                    cudaStream_t st) {
     const uint32_t nq = q1 - q0;
     const uint32_t k = ix->term_size;
     if (std::isnan(threshold)) throw Err{ COBSGPU_ERR_INVALID_ARG, "threshold is NaN" };
     // Streaming workloads (fixed-length reads) present the same offsets batch after batch:
-    // the derived geometry is cached and, when the device copy of this buffer set is current,
-    // only the flag words are re-armed on the device instead of a rebuild + upload.
-    const bool same = ix->geo_version != 0 && ix->geo_offsets.size() == static_cast<size_t>(nq) + 1 &&
-                      ix->geo_threshold == threshold &&
-                      std::memcmp(ix->geo_offsets.data(), offsets + q0, (static_cast<size_t>(nq) + 1) * 8) == 0;
+    // the derived geometry is cached per slot and, when the device copy is current, only the
+    // flag words are re-armed on the device instead of a rebuild + upload.
+    const bool same = sl.geo_valid && sl.geo_offsets.size() == static_cast<size_t>(nq) + 1 &&
+                      sl.geo_threshold == threshold &&
+                      std::memcmp(sl.geo_offsets.data(), offsets + q0, (static_cast<size_t>(nq) + 1) * 8) == 0;
     if (!same) {
-        ix->geo_version = 0;   // stays invalid if one of the checks below throws
-        ix->b_nq = nq;
-        ix->b_qoff.resize(nq + 1);
-        ix->b_koff.resize(nq + 1);
-        ix->b_thr.resize(nq);
+        sl.geo_valid = false;   // stays invalid if one of the checks below throws
+        sl.meta_resident = false;
+        sl.nq = nq;
+        sl.qoff.resize(nq + 1);
+        sl.koff.resize(nq + 1);
+        sl.thr.resize(nq);
         const uint64_t base0 = offsets[q0];
-        uint64_t km = 0, last_T = ~0ull;
+        uint64_t km = 0, last_T = ~0ull, max_T = 0;
         uint32_t uT = 0, last_thr = 0;
         bool uniform = true;
         for (uint32_t i = 0; i < nq; ++i) {
@@ -630,9 +709,10 @@ void prepare_batch(cobsgpu_index* ix, const char* queries, bool dev_queries,
                                " characters long (query " + std::to_string(q0 + i) + ")" };
             const uint64_t T = len - k + 1;
             if (T >= 0xFFFFFFFFull) throw Err{ COBSGPU_ERR_INVALID_ARG, "query too long" };
-            ix->b_qoff[i] = offsets[q0 + i] - base0;
-            ix->b_koff[i] = static_cast<uint32_t>(km);
+            sl.qoff[i] = offsets[q0 + i] - base0;
+            sl.koff[i] = static_cast<uint32_t>(km);
             km += T;
+            max_T = std::max(max_T, T);
             if (i == 0) uT = static_cast<uint32_t>(T);
             else if (T != uT) uniform = false;
             if (T != last_T) {
@@ -641,79 +721,75 @@ void prepare_batch(cobsgpu_index* ix, const char* queries, bool dev_queries,
                 last_thr = th <= 0.0 ? 0u : (th >= 4294967295.0 ? 0xFFFFFFFFu : static_cast<uint32_t>(th));
                 last_T = T;
             }
-            ix->b_thr[i] = last_thr;
+            sl.thr[i] = last_thr;
         }
         if (km > 0x7FFFFFFFull)
             throw Err{ COBSGPU_ERR_INVALID_ARG, "batch holds more than 2^31 k-mers" };
-        ix->b_qoff[nq] = offsets[q1] - base0;
-        ix->b_koff[nq] = static_cast<uint32_t>(km);
-        ix->b_total_kmers = static_cast<uint32_t>(km);
-        ix->b_uniform_T = uniform ? uT : 0;
-        ix->geo_offsets.assign(offsets + q0, offsets + q1 + 1);
-        ix->geo_threshold = threshold;
-        ix->geo_version = ++ix->geo_counter;
+        sl.qoff[nq] = offsets[q1] - base0;
+        sl.koff[nq] = static_cast<uint32_t>(km);
+        sl.total_kmers = static_cast<uint32_t>(km);
+        sl.uniform_T = uniform ? uT : 0;
+        sl.max_T = static_cast<uint32_t>(max_T);
+        sl.geo_offsets.assign(offsets + q0, offsets + q1 + 1);
+        sl.geo_threshold = threshold;
+        sl.geo_valid = true;
     }
     const uint64_t base = offsets[q0];
-    const uint64_t kmers = ix->b_total_kmers;
-    const uint32_t uniform_T = ix->b_uniform_T;
-    const uint64_t blob_bytes = ix->b_qoff[nq];
+    const uint64_t kmers = sl.total_kmers;
+    const uint64_t blob_bytes = sl.qoff[nq];
 
     {
         PhaseScope ps(ix, PH_H2D, st);
         if (dev_queries) {
-            ix->b_dev_queries = queries + base;
+            sl.dev_queries = queries + base;
         } else {
-            ix->d_queries.ensure(blob_bytes + 16);
-            CK(cudaMemcpyAsync(ix->d_queries.p, queries + base, blob_bytes, cudaMemcpyHostToDevice, st));
-            ix->b_dev_queries = ix->d_queries.as<char>();
+            sl.d_queries.ensure(blob_bytes + 16);
+            CK(cudaMemcpyAsync(sl.d_queries.p, queries + base, blob_bytes, cudaMemcpyHostToDevice, st));
+            sl.dev_queries = sl.d_queries.as<char>();
         }
         // one block: flags (2 x int) | bad (nq x u32) | qoff | koff | thr.  flags and bad are
         // "clear" when every byte is 0x7F, so one memset re-arms them.
         const size_t nq1 = std::max<size_t>(nq, 1);
-        ix->meta_bad = 8;
-        ix->meta_qoff = round_up<size_t>(ix->meta_bad + nq1 * 4, 8);
-        ix->meta_koff = ix->meta_qoff + (static_cast<size_t>(nq) + 1) * 8;
-        ix->meta_thr = ix->meta_koff + round_up<size_t>((static_cast<size_t>(nq) + 1) * 4, 8);
-        const size_t meta_bytes = ix->meta_thr + nq1 * 4;
-        const size_t arm_bytes = ix->meta_bad + nq1 * 4;
-        ix->meta().ensure(meta_bytes);
-        const int set = ix->cur;
-        if (ix->meta_version[set] == ix->geo_version && ix->meta_ptr[set] == ix->meta().p) {
-            CK(cudaMemsetAsync(ix->meta().p, 0x7F, arm_bytes, st));
+        sl.meta_bad = 8;
+        sl.meta_qoff = round_up<size_t>(sl.meta_bad + nq1 * 4, 8);
+        sl.meta_koff = sl.meta_qoff + (static_cast<size_t>(nq) + 1) * 8;
+        sl.meta_thr = sl.meta_koff + round_up<size_t>((static_cast<size_t>(nq) + 1) * 4, 8);
+        const size_t meta_bytes = sl.meta_thr + nq1 * 4;
+        const size_t arm_bytes = sl.meta_bad + nq1 * 4;
+        sl.d_meta.ensure(meta_bytes);
+        if (sl.meta_resident && sl.meta_ptr == sl.d_meta.p) {
+            CK(cudaMemsetAsync(sl.d_meta.p, 0x7F, arm_bytes, st));
         } else {
-            const int slot = ix->meta_slot;
-            ix->meta_slot = (slot + 1) % cobsgpu_index::META_RING;
-            if (!ix->meta_ev[slot]) CK(cudaEventCreateWithFlags(&ix->meta_ev[slot], cudaEventDisableTiming));
-            else CK(cudaEventSynchronize(ix->meta_ev[slot]));   // previous upload from this slot done
-            ix->h_meta[slot].ensure(meta_bytes);
-            char* hm = ix->h_meta[slot].as<char>();
+            if (sl.ev_meta) CK(cudaEventSynchronize(sl.ev_meta));   // previous upload out of h_meta done
+            sl.h_meta.ensure(meta_bytes);
+            char* hm = sl.h_meta.as<char>();
             std::memset(hm, 0x7F, arm_bytes);
-            std::memcpy(hm + ix->meta_qoff, ix->b_qoff.data(), (static_cast<size_t>(nq) + 1) * 8);
-            std::memcpy(hm + ix->meta_koff, ix->b_koff.data(), (static_cast<size_t>(nq) + 1) * 4);
-            if (nq) std::memcpy(hm + ix->meta_thr, ix->b_thr.data(), static_cast<size_t>(nq) * 4);
-            CK(cudaMemcpyAsync(ix->meta().p, hm, meta_bytes, cudaMemcpyHostToDevice, st));
-            CK(cudaEventRecord(ix->meta_ev[slot], st));
-            ix->meta_version[set] = ix->geo_version;
-            ix->meta_ptr[set] = ix->meta().p;
+            std::memcpy(hm + sl.meta_qoff, sl.qoff.data(), (static_cast<size_t>(nq) + 1) * 8);
+            std::memcpy(hm + sl.meta_koff, sl.koff.data(), (static_cast<size_t>(nq) + 1) * 4);
+            if (nq) std::memcpy(hm + sl.meta_thr, sl.thr.data(), static_cast<size_t>(nq) * 4);
+            CK(cudaMemcpyAsync(sl.d_meta.p, hm, meta_bytes, cudaMemcpyHostToDevice, st));
+            CK(cudaEventRecord(sl.ev(sl.ev_meta), st));
+            sl.meta_resident = true;
+            sl.meta_ptr = sl.d_meta.p;
         }
     }
-    ix->hashes().ensure(std::max<uint64_t>(1, kmers) * ix->num_hashes * 8);
+    sl.d_hashes.ensure(std::max<uint64_t>(1, kmers) * ix->num_hashes * 8);
     if (kmers) {
         HashParams hp{};
-        hp.queries = ix->b_dev_queries;
-        hp.qoff = ix->d_qoff();
-        hp.koff = ix->d_koff();
+        hp.queries = sl.dev_queries;
+        hp.qoff = sl.d_qoff();
+        hp.koff = sl.d_koff();
         hp.nq = nq;
-        hp.total_kmers = ix->b_total_kmers;
-        hp.uniform_T = uniform_T;
+        hp.total_kmers = sl.total_kmers;
+        hp.uniform_T = sl.uniform_T;
         hp.k = k;
         hp.h = ix->num_hashes;
         hp.canonicalize = ix->canonicalize;
-        hp.hashes = ix->hashes().as<uint64_t>();
-        hp.first_bad = ix->d_flags();
-        hp.bad = ix->d_bad();
+        hp.hashes = sl.d_hashes.as<uint64_t>();
+        hp.first_bad = sl.d_flags();
+        hp.bad = sl.d_bad();
         PhaseScope ps(ix, PH_HASH, st);
-        const uint32_t grid = div_ceil<uint32_t>(ix->b_total_kmers, 128);
+        const uint32_t grid = div_ceil<uint32_t>(sl.total_kmers, 128);
         // k = 31 is what COBS indices use in practice: k-mer bytes held in registers
         if (k == 31) hash_kmers_kernel<31><<<grid, 128, 0, st>>>(hp);
         else hash_kmers_kernel<0><<<grid, 128, 0, st>>>(hp);
@@ -724,18 +800,18 @@ void prepare_batch(cobsgpu_index* ix, const char* queries, bool dev_queries,
     ix->tm.queries += nq;
 }
 
-ScoreParams base_params(cobsgpu_index* ix, const uint32_t* d_qlist, uint32_t n_slots) {
+// `src` holds the batch (hashes + metadata), the candidate buffers may belong to another slot
+ScoreParams base_params(cobsgpu_index* ix, const Slot& src, const uint32_t* d_qlist, uint32_t n_slots) {
     ScoreParams sp{};
     sp.tiles = ix->d_tiles;
     sp.n_tiles = static_cast<uint32_t>(ix->tiles.size());
     sp.h = ix->num_hashes;
-    sp.hashes = ix->hashes().as<uint64_t>();
-    sp.koff = ix->d_koff();
+    sp.hashes = src.d_hashes.as<uint64_t>();
+    sp.koff = src.d_koff();
     sp.qlist = d_qlist;
     sp.nq_items = n_slots;
-    sp.thr = ix->d_thr();
+    sp.thr = src.d_thr();
     sp.dense_pitch = ix->dense_pitch;
-    sp.work = ix->d_work;
     return sp;
 }
 
@@ -748,67 +824,39 @@ uint32_t bits_for(uint32_t v) {
     return std::max<uint32_t>(b, 1);
 }
 
-// One pass over `n_slots` queries (slot i = batch query qlist[i], or i when d_qlist is null):
-// K2 (+ dense_to_cand for long queries) fills the candidate lists, K3 sorts them.  Leaves
-// d_cand_count / d_res_count per slot and the sorted keys in d_cand (or d_scratch, see
-// *large_in_scratch).  max_T = largest k-mer count among the slots.
-void run_pass(cobsgpu_index* ix, const uint32_t* d_qlist, uint32_t n_slots, uint32_t cap,
-              bool long_mode, uint32_t max_T, uint64_t limit, bool* large_in_scratch,
-              cudaStream_t st) {
-    cap = std::max<uint32_t>(cap, 1);
-    ix->d_cand.ensure(static_cast<uint64_t>(n_slots) * cap * 8);
-    ix->d_cand_count.ensure(n_slots * 4);
-    ix->d_res_count.ensure(n_slots * 4);
-    CK(cudaMemsetAsync(ix->d_cand_count.p, 0, n_slots * 4, st));
-    ScoreParams sp = base_params(ix, d_qlist, n_slots);
-    sp.cand_count = ix->d_cand_count.as<uint32_t>();
-    sp.cand = ix->d_cand.as<uint64_t>();
-    sp.cap = cap;
-    if (!long_mode) {
-        launch_score(ix, sp, MODE_CAND, st);
-    } else {
-        ix->d_dense.ensure(static_cast<uint64_t>(n_slots) * ix->dense_pitch * 4);
-        CK(cudaMemsetAsync(ix->d_dense.p, 0, static_cast<uint64_t>(n_slots) * ix->dense_pitch * 4, st));
-        sp.dense32 = ix->d_dense.as<uint32_t>();
-        launch_score(ix, sp, MODE_DENSE32, st);
-        if (!ix->pages.empty()) {
-            PhaseScope ps(ix, PH_SELECT, st);
-            DenseToCandParams dp{};
-            dp.dense32 = sp.dense32;
-            dp.dense_pitch = ix->dense_pitch;
-            dp.qlist = d_qlist;
-            dp.thr = ix->d_thr();
-            const uint32_t np = static_cast<uint32_t>(ix->pages.size());
-            dp.seg_dense_off = ix->d_seg;
-            dp.seg_n_real = ix->d_seg + np;
-            dp.seg_doc_base = ix->d_seg + 2 * np;
-            dp.n_seg = np;
-            dp.cand_count = sp.cand_count;
-            dp.cand = sp.cand;
-            dp.cap = cap;
-            uint32_t max_real = 1;
-            for (auto& lp : ix->pages) max_real = std::max(max_real, lp.n_real);
-            dim3 grid(std::min<uint32_t>(div_ceil<uint32_t>(max_real, 256), 64), n_slots);
-            dense_to_cand_kernel<<<grid, 256, 0, st>>>(dp);
-            CK(cudaGetLastError());
-            ix->tm.kernel_launches++;
-        }
-    }
+uint32_t pow2_ceil(uint32_t v) {
+    uint32_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// How one pass turns scores into candidate lists.
+struct PassPlan {
+    int mode = MODE_CAND;     // MODE_CAND / MODE_TOPK / MODE_DENSE32 (queries beyond 16 planes)
+    bool lng = false;         // 16 bit-planes
+    uint32_t cap = 1;         // candidate slots per query
+    uint64_t limit = 0;       // results wanted per query (0 = all)
+};
+
+// K3 of one pass: (radix sort of the long lists) + finalize.  Candidates of slot i are at
+// cand + i * cap with their number in cand_count[i]; the first min(n, limit) sorted keys end up
+// at out_keys + i * stride, the count (or a COUNT_* flag) in out_counts[i].
+void launch_select(cobsgpu_index* ix, const Slot& src, Slot& work, const uint32_t* d_qlist,
+                   uint32_t n_slots, const PassPlan& pl, uint32_t max_T, uint32_t* cand_count,
+                   uint64_t* out_keys, uint32_t* out_counts, uint32_t stride, bool report_bad,
+                   cudaStream_t st) {
     PhaseScope ps(ix, PH_SELECT, st);
-    result_counts_kernel<<<div_ceil<uint32_t>(n_slots, 256), 256, 0, st>>>(
-        sp.cand_count, n_slots, cap, limit, ix->d_res_count.as<uint32_t>(), ix->d_flags() + 1);
-    CK(cudaGetLastError());
-    sort_small_kernel<<<n_slots, SORT_SMALL_THREADS, 0, st>>>(sp.cand, sp.cand_count, cap);
-    CK(cudaGetLastError());
-    ix->tm.kernel_launches += 2;
-    *large_in_scratch = false;
-    if (cap > SORT_SMALL_MAX) {
-        ix->d_scratch.ensure(static_cast<uint64_t>(n_slots) * cap * 8);
+    const uint32_t cap = pl.cap;
+    uint64_t* cand = work.d_cand.as<uint64_t>();
+    bool large_in_scratch = false;
+    if (cap > FIN_SORT_MAX) {
+        work.d_scratch.ensure(static_cast<uint64_t>(n_slots) * cap * 8);
         SortLargeParams lp{};
-        lp.cand = sp.cand;
-        lp.scratch = ix->d_scratch.as<uint64_t>();
-        lp.cand_count = sp.cand_count;
+        lp.cand = cand;
+        lp.scratch = work.d_scratch.as<uint64_t>();
+        lp.cand_count = cand_count;
         lp.cap = cap;
+        lp.min_n = FIN_SORT_MAX;
         // digits over the varying key bits only: document id (low word) then ~score
         const uint32_t doc_bits = bits_for(ix->shard_doc_end ? ix->shard_doc_end - 1 : 0);
         const uint32_t score_bits = bits_for(max_T);
@@ -816,11 +864,99 @@ void run_pass(cobsgpu_index* ix, const uint32_t* d_qlist, uint32_t n_slots, uint
         for (uint32_t b = 0; b < doc_bits; b += 8) lp.digit_shift[n++] = b;
         for (uint32_t b = 0; b < score_bits; b += 8) lp.digit_shift[n++] = 32 + b;
         lp.n_pass = n;
-        *large_in_scratch = (n & 1) != 0;
+        large_in_scratch = (n & 1) != 0;
         sort_large_kernel<<<n_slots, SORT_LARGE_THREADS, 0, st>>>(lp);
         CK(cudaGetLastError());
         ix->tm.kernel_launches++;
     }
+    FinalizeParams fp{};
+    fp.cand = cand;
+    fp.scratch = work.d_scratch.as<uint64_t>();
+    fp.cand_count = cand_count;
+    fp.bad = report_bad ? src.d_bad() : nullptr;
+    fp.qlist = d_qlist;
+    fp.cap = cap;
+    fp.nq = n_slots;
+    fp.limit = pl.limit;
+    fp.out_keys = out_keys;
+    fp.out_counts = out_counts;
+    fp.stride = stride;
+    fp.fin_sort_max = std::min<uint32_t>(FIN_SORT_MAX, pow2_ceil(std::max<uint32_t>(cap, 32)));
+    fp.large_in_scratch = large_in_scratch ? 1 : 0;
+    const size_t smem = static_cast<size_t>(fp.fin_sort_max) * 8;
+    static bool attr_set[64] = {};
+    if (!attr_set[ix->device & 63]) {
+        CK(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(FIN_SORT_MAX * 8)));
+        attr_set[ix->device & 63] = true;
+    }
+    finalize_kernel<<<div_ceil<uint32_t>(n_slots, FIN_WARPS), FIN_WARPS * 32, smem, st>>>(fp);
+    CK(cudaGetLastError());
+    ix->tm.kernel_launches++;
+}
+
+// K2 of one pass over `n_slots` queries of the batch in `src` (slot i = batch query qlist[i],
+// or i when d_qlist is null): fills work.d_cand / cand_count (zeroed here).
+void launch_pass_score(cobsgpu_index* ix, const Slot& src, Slot& work, const uint32_t* d_qlist,
+                       uint32_t n_slots, const PassPlan& pl, uint32_t* cand_count, cudaStream_t st) {
+    const uint32_t cap = pl.cap;
+    work.d_cand.ensure(static_cast<uint64_t>(n_slots) * cap * 8);
+    CK(cudaMemsetAsync(cand_count, 0, static_cast<size_t>(n_slots) * 4, st));
+    ScoreParams sp = base_params(ix, src, d_qlist, n_slots);
+    sp.cand_count = cand_count;
+    sp.cand = work.d_cand.as<uint64_t>();
+    sp.cap = cap;
+    sp.topk = static_cast<uint32_t>(std::min<uint64_t>(pl.limit, 0xFFFFFFFFull));
+    if (pl.mode != MODE_DENSE32) {
+        launch_score(ix, sp, pl.mode, pl.lng, st);
+        return;
+    }
+    // queries beyond the 16 bit-planes: u32 scores flushed to global memory, then thresholded
+    work.d_dense.ensure(static_cast<uint64_t>(n_slots) * ix->dense_pitch * 4);
+    CK(cudaMemsetAsync(work.d_dense.p, 0, static_cast<uint64_t>(n_slots) * ix->dense_pitch * 4, st));
+    sp.dense32 = work.d_dense.as<uint32_t>();
+    launch_score(ix, sp, MODE_DENSE32, false, st);
+    if (ix->pages.empty()) return;
+    PhaseScope ps(ix, PH_SELECT, st);
+    DenseToCandParams dp{};
+    dp.dense32 = sp.dense32;
+    dp.dense_pitch = ix->dense_pitch;
+    dp.qlist = d_qlist;
+    dp.thr = src.d_thr();
+    const uint32_t np = static_cast<uint32_t>(ix->pages.size());
+    dp.seg_dense_off = ix->d_seg;
+    dp.seg_n_real = ix->d_seg + np;
+    dp.seg_doc_base = ix->d_seg + 2 * np;
+    dp.n_seg = np;
+    dp.cand_count = sp.cand_count;
+    dp.cand = sp.cand;
+    dp.cap = cap;
+    uint32_t max_real = 1;
+    for (auto& lp : ix->pages) max_real = std::max(max_real, lp.n_real);
+    dim3 grid(std::min<uint32_t>(div_ceil<uint32_t>(max_real, 256), 64), n_slots);
+    dense_to_cand_kernel<<<grid, 256, 0, st>>>(dp);
+    CK(cudaGetLastError());
+    ix->tm.kernel_launches++;
+}
+
+// CSR formatting in `work.d_out` (layout_out(n_slots) done by the caller): offsets + keys
+void launch_csr(cobsgpu_index* ix, const Slot& src, Slot& work, uint32_t n_slots, uint32_t cap,
+                cudaStream_t st) {
+    PhaseScope ps(ix, PH_SELECT, st);
+    scan_offsets_kernel<<<1, 1024, 0, st>>>(work.d_res_count.as<uint32_t>(), n_slots, work.o_off());
+    CK(cudaGetLastError());
+    GatherKeysParams gp{ work.d_cand.as<uint64_t>(), work.d_res_count.as<uint32_t>(), work.o_off(),
+                         cap, work.o_keys(), src.d_flags(), work.o_flags() };
+    gather_keys_kernel<<<n_slots, 256, 0, st>>>(gp);
+    CK(cudaGetLastError());
+    ix->tm.kernel_launches += 2;
+}
+
+// bytes of d_out a pass over n_slots queries can need: header + every list at its longest
+size_t out_bytes(Slot& work, uint32_t n_slots, const PassPlan& pl) {
+    work.layout_out(n_slots);
+    const uint64_t per = pl.limit ? std::min<uint64_t>(pl.limit, pl.cap) : pl.cap;
+    return work.out_keys + static_cast<size_t>(n_slots) * per * 8;
 }
 
 struct HostList {
@@ -828,181 +964,283 @@ struct HostList {
     std::vector<uint32_t> doc, score;
 };
 
-// CSR formatting of a finished pass + copy to the host (slot order)
-void fetch_pass(cobsgpu_index* ix, const uint32_t* d_qlist, uint32_t n_slots, uint32_t cap,
-                bool large_in_scratch, HostList* out, std::vector<uint32_t>* cand_counts,
-                cudaStream_t st) {
-    {
-        PhaseScope ps(ix, PH_SELECT, st);
-        ix->d_offsets.ensure((n_slots + 1) * 8);
-        scan_offsets_kernel<<<1, 1024, 0, st>>>(ix->d_res_count.as<uint32_t>(), n_slots,
-                                                ix->d_offsets.as<uint64_t>());
-        CK(cudaGetLastError());
-        ix->tm.kernel_launches++;
+void decode_keys(const uint64_t* keys, uint64_t n, uint32_t* doc, uint32_t* score) {
+    for (uint64_t i = 0; i < n; ++i) {
+        doc[i] = key_doc(keys[i]);
+        score[i] = key_score(keys[i]);
     }
-    out->off.resize(n_slots + 1);
-    cand_counts->resize(n_slots);
-    {
-        PhaseScope ps(ix, PH_D2H, st);
-        ix->h_off.ensure((n_slots + 1) * 8);
-        ix->h_counts.ensure(n_slots * 4);
-        CK(cudaMemcpyAsync(ix->h_off.p, ix->d_offsets.p, (n_slots + 1) * 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(ix->h_counts.p, ix->d_cand_count.p, n_slots * 4, cudaMemcpyDeviceToHost, st));
-    }
-    CK(cudaStreamSynchronize(st));
-    std::memcpy(out->off.data(), ix->h_off.p, (n_slots + 1) * 8);
-    std::memcpy(cand_counts->data(), ix->h_counts.p, n_slots * 4);
-    const uint64_t total = out->off[n_slots];
-    out->doc.resize(total);
-    out->score.resize(total);
-    if (total == 0) return;
-    ix->d_out_doc.ensure(total * 4);
-    ix->d_out_score.ensure(total * 4);
-    {
-        PhaseScope ps(ix, PH_SELECT, st);
-        GatherParams gp{};
-        gp.cand = ix->d_cand.as<uint64_t>();
-        gp.scratch = ix->d_scratch.as<uint64_t>();
-        gp.cand_count = ix->d_cand_count.as<uint32_t>();
-        gp.res_count = ix->d_res_count.as<uint32_t>();
-        gp.qlist = nullptr;   // CSR is in slot order
-        gp.cap = cap;
-        gp.large_in_scratch = large_in_scratch ? 1 : 0;
-        gp.offsets = ix->d_offsets.as<uint64_t>();
-        gp.out_doc = ix->d_out_doc.as<uint32_t>();
-        gp.out_score = ix->d_out_score.as<uint32_t>();
-        gather_kernel<<<n_slots, 256, 0, st>>>(gp);
-        CK(cudaGetLastError());
-        ix->tm.kernel_launches++;
-    }
-    {
-        PhaseScope ps(ix, PH_D2H, st);
-        ix->h_doc.ensure(total * 4);
-        ix->h_score.ensure(total * 4);
-        CK(cudaMemcpyAsync(ix->h_doc.p, ix->d_out_doc.p, total * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(ix->h_score.p, ix->d_out_score.p, total * 4, cudaMemcpyDeviceToHost, st));
-    }
-    CK(cudaStreamSynchronize(st));
-    std::memcpy(out->doc.data(), ix->h_doc.p, total * 4);
-    std::memcpy(out->score.data(), ix->h_score.p, total * 4);
 }
 
-void check_bad_base(cobsgpu_index* ix, uint32_t q0, cudaStream_t st) {
-    int flags[2];
-    CK(cudaMemcpyAsync(flags, ix->d_flags(), sizeof(flags), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    if (flags[0] != FLAG_CLEAR)
-        throw Err{ COBSGPU_ERR_INVALID_BASE,
-                   "Invalid DNA base pair in query string. Only ACGT are allowed. (query " +
-                       std::to_string(q0 + flags[0]) + ")" };
+void throw_bad_base(uint32_t query) {
+    throw Err{ COBSGPU_ERR_INVALID_BASE,
+               "Invalid DNA base pair in query string. Only ACGT are allowed. (query " +
+                   std::to_string(query) + ")" };
 }
 
-const uint32_t* upload_qlist(cobsgpu_index* ix, const std::vector<uint32_t>& ids, size_t begin,
-                             size_t n, cudaStream_t st) {
-    ix->d_qlist.ensure(std::max<size_t>(n, 1) * 4);
-    CK(cudaMemcpyAsync(ix->d_qlist.p, ids.data() + begin, n * 4, cudaMemcpyHostToDevice, st));
-    return ix->d_qlist.as<uint32_t>();
+const uint32_t* upload_qlist(Slot& work, const std::vector<uint32_t>& ids, size_t begin, size_t n,
+                             cudaStream_t st) {
+    work.d_qlist.ensure(std::max<size_t>(n, 1) * 4);
+    CK(cudaMemcpyAsync(work.d_qlist.p, ids.data() + begin, n * 4, cudaMemcpyHostToDevice, st));
+    return work.d_qlist.as<uint32_t>();
 }
 
-// exhaustive pass over the given batch queries in workspace-bounded sub-batches; every real
-// document of the shard can become a candidate (cap = shard_real_docs)
-void run_exhaustive(cobsgpu_index* ix, const std::vector<uint32_t>& ids, bool long_mode,
+// Synchronous exhaustive pass over the given queries of the batch in `src`, in workspace-bounded
+// sub-batches through the aux buffers: every real document of the shard can become a candidate
+// (cap = shard_real_docs), so nothing is ever dropped.  Used for threshold <= 0 without a small
+// limit, for queries whose candidates overflowed the fused path, and for queries beyond 16 planes.
+void run_exhaustive(cobsgpu_index* ix, const Slot& src, const std::vector<uint32_t>& ids,
                     uint64_t limit, std::vector<HostList>* lists,
-                    std::vector<std::pair<uint32_t, uint32_t>>* where, cudaStream_t st) {
+                    std::vector<std::pair<uint32_t, uint32_t>>* where) {
     if (ids.empty()) return;
-    const uint32_t cap = std::max<uint32_t>(ix->shard_real_docs, 1);
-    uint64_t per_q = static_cast<uint64_t>(cap) * 8 * (cap > SORT_SMALL_MAX ? 2 : 1);
-    if (long_mode) per_q += ix->dense_pitch * 4;
+    cudaStream_t st = ix->stream;
+    Slot& work = ix->aux;
+    PassPlan pl;
+    pl.cap = std::max<uint32_t>(ix->shard_real_docs, 1);
+    pl.limit = limit;
+    uint64_t per_q = static_cast<uint64_t>(pl.cap) * 8 * (pl.cap > FIN_SORT_MAX ? 2 : 1) +
+                     (limit ? std::min<uint64_t>(limit, pl.cap) : pl.cap) * 8;
     const size_t sub = static_cast<size_t>(
         std::max<uint64_t>(1, std::min<uint64_t>(ids.size(), ix->workspace_bytes / std::max<uint64_t>(per_q, 1))));
     for (size_t b = 0; b < ids.size(); b += sub) {
-        const size_t n = std::min(sub, ids.size() - b);
-        const uint32_t* d_ql = upload_qlist(ix, ids, b, n, st);
+        const uint32_t n = static_cast<uint32_t>(std::min(sub, ids.size() - b));
+        const uint32_t* d_ql = upload_qlist(work, ids, b, n, st);
         uint32_t max_T = 1;
         for (size_t i = 0; i < n; ++i)
-            max_T = std::max(max_T, ix->b_koff[ids[b + i] + 1] - ix->b_koff[ids[b + i]]);
-        bool lis = false;
-        run_pass(ix, d_ql, static_cast<uint32_t>(n), cap, long_mode, max_T, limit, &lis, st);
+            max_T = std::max(max_T, src.koff[ids[b + i] + 1] - src.koff[ids[b + i]]);
+        pl.lng = max_T > MAX_T_SHORT;
+        pl.mode = max_T > MAX_T_LONG ? MODE_DENSE32 : MODE_CAND;
+        work.d_out.ensure(out_bytes(work, n, pl));
+        work.d_res_count.ensure(static_cast<size_t>(n) * 4);
+        launch_pass_score(ix, src, work, d_ql, n, pl, work.o_cc(), st);
+        launch_select(ix, src, work, d_ql, n, pl, max_T, work.o_cc(), work.d_cand.as<uint64_t>(),
+                      work.d_res_count.as<uint32_t>(), pl.cap, false, st);
+        launch_csr(ix, src, work, n, pl.cap, st);
+        // header first (it tells how many keys there are), then the keys
+        work.h_out.ensure(work.out_keys);
+        {
+            PhaseScope ps(ix, PH_D2H, st);
+            CK(cudaMemcpyAsync(work.h_out.p, work.d_out.p, work.out_keys, cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaStreamSynchronize(st));
         lists->emplace_back();
-        std::vector<uint32_t> counts;
-        fetch_pass(ix, d_ql, static_cast<uint32_t>(n), cap, lis, &lists->back(), &counts, st);
+        HostList& L = lists->back();
+        const uint64_t* off = reinterpret_cast<const uint64_t*>(work.h_out.as<char>() + work.out_off);
+        L.off.assign(off, off + n + 1);
+        const uint64_t total = L.off[n];
+        L.doc.resize(total);
+        L.score.resize(total);
+        if (total) {
+            work.h_out.ensure(work.out_keys + total * 8);
+            {
+                PhaseScope ps(ix, PH_D2H, st);
+                CK(cudaMemcpyAsync(work.h_out.as<char>() + work.out_keys, work.o_keys(), total * 8,
+                                   cudaMemcpyDeviceToHost, st));
+            }
+            CK(cudaStreamSynchronize(st));
+            decode_keys(reinterpret_cast<const uint64_t*>(work.h_out.as<char>() + work.out_keys), total,
+                        L.doc.data(), L.score.data());
+        }
         for (size_t i = 0; i < n; ++i)
             (*where)[ids[b + i]] = { static_cast<uint32_t>(lists->size() - 1), static_cast<uint32_t>(i) };
     }
 }
 
-void search_one_batch(cobsgpu_index* ix, const char* queries, const uint64_t* offsets, uint32_t q0,
-                      uint32_t q1, double threshold, uint64_t limit) {
-    cudaStream_t st = ix->stream;
-    prepare_batch(ix, queries, false, offsets, q0, q1, threshold, st);
-    const uint32_t nq = q1 - q0;
-    std::vector<uint32_t> short_ids, long_ids;
-    for (uint32_t i = 0; i < nq; ++i) {
-        const uint32_t T = ix->b_koff[i + 1] - ix->b_koff[i];
-        (T > 255 ? long_ids : short_ids).push_back(i);
+// The plan of a batch's main pass, from the request and the batch geometry:
+//   a small limit        -> TOPK (bounded candidate lists, can never overflow)
+//   threshold > 0        -> CAND with `max_candidates` slots per query (overflow -> redone)
+//   otherwise            -> no main pass: every document passes, exhaustive at collect
+// Queries beyond 16 bit-planes never take part in the main pass.
+bool plan_main_pass(const cobsgpu_index* ix, const Slot& sl, double threshold, uint64_t limit,
+                    uint32_t main_max_T, PassPlan* pl) {
+    pl->lng = main_max_T > MAX_T_SHORT;
+    pl->limit = limit;
+    const uint32_t real = std::max<uint32_t>(ix->shard_real_docs, 1);
+    if (limit >= 1 && limit <= TOPK_MAX_K) {
+        const uint64_t cap = std::min<uint64_t>(static_cast<uint64_t>(ix->warps_per_query) * limit, real);
+        // the candidate buffer of one batch must fit the workspace (batches are cut accordingly)
+        if (cap * 8 <= ix->workspace_bytes) {
+            pl->mode = MODE_TOPK;
+            pl->cap = static_cast<uint32_t>(std::max<uint64_t>(cap, 1));
+            return true;
+        }
     }
+    if (threshold > 0.0) {
+        pl->mode = MODE_CAND;
+        pl->cap = std::min<uint32_t>(ix->max_candidates, real);
+        return true;
+    }
+    (void)sl;
+    return false;
+}
+
+Slot& take_slot(cobsgpu_index* ix) {
+    Slot& sl = ix->slots[ix->next_slot];
+    if (sl.busy)
+        throw Err{ COBSGPU_ERR_INVALID_ARG,
+                   "too many batches in flight: collect a ticket before submitting another" };
+    ix->next_slot = (ix->next_slot + 1) % cobsgpu_index::N_SLOTS;
+    return sl;
+}
+
+// Enqueues queries [q0, q1) of the caller's batch: upload + K1 on s_in, K2 + K3 on the main
+// stream, header + a speculative prefix of the keys back to pinned memory on s_out.  Nothing
+// here waits for the device.
+Slot& submit_batch(cobsgpu_index* ix, const char* queries, const uint64_t* offsets, uint32_t q0,
+                   uint32_t q1, double threshold, uint64_t limit) {
+    Slot& sl = take_slot(ix);
+    prepare_batch(ix, sl, queries, false, offsets, q0, q1, threshold, ix->s_in);
+    CK(cudaEventRecord(sl.ev(sl.ev_in), ix->s_in));
+    const uint32_t nq = q1 - q0;
+    sl.q0 = q0;
+    sl.threshold = threshold;
+    sl.limit = limit;
+    sl.main_ids.clear();
+    sl.huge_ids.clear();
+    uint32_t main_max_T = sl.max_T;
+    if (sl.max_T > MAX_T_LONG) {
+        main_max_T = 1;
+        for (uint32_t i = 0; i < nq; ++i) {
+            const uint32_t T = sl.koff[i + 1] - sl.koff[i];
+            if (T > MAX_T_LONG) sl.huge_ids.push_back(i);
+            else {
+                sl.main_ids.push_back(i);
+                main_max_T = std::max(main_max_T, T);
+            }
+        }
+    }
+    const uint32_t n_main = sl.huge_ids.empty() ? nq : static_cast<uint32_t>(sl.main_ids.size());
+    PassPlan pl;
+    sl.mode = -1;
+    sl.busy = true;
+    sl.ticket = ++ix->ticket_counter;
+    cudaStream_t st = ix->stream;
+    CK(cudaStreamWaitEvent(st, sl.ev_in, 0));
+    if (n_main == 0 || !plan_main_pass(ix, sl, threshold, limit, main_max_T, &pl)) {
+        // exhaustive at collect; only the invalid-base flag is needed from the device
+        sl.layout_out(0);
+        sl.d_out.ensure(sl.out_keys);
+        sl.h_out.ensure(sl.out_keys);
+        CK(cudaMemcpyAsync(sl.h_out.p, sl.d_flags(), 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(sl.ev(sl.ev_out), st));
+        return sl;
+    }
+    sl.mode = pl.mode;
+    sl.lng = pl.lng;
+    sl.cap = pl.cap;
+    const uint32_t* d_ql = sl.huge_ids.empty() ? nullptr : upload_qlist(sl, sl.main_ids, 0, n_main, st);
+    const size_t ob = out_bytes(sl, n_main, pl);
+    sl.d_out.ensure(ob);
+    sl.d_res_count.ensure(static_cast<size_t>(n_main) * 4);
+    launch_pass_score(ix, sl, sl, d_ql, n_main, pl, sl.o_cc(), st);
+    launch_select(ix, sl, sl, d_ql, n_main, pl, main_max_T, sl.o_cc(), sl.d_cand.as<uint64_t>(),
+                  sl.d_res_count.as<uint32_t>(), pl.cap, false, st);
+    launch_csr(ix, sl, sl, n_main, pl.cap, st);
+    CK(cudaEventRecord(sl.ev(sl.ev_main), st));
+    // ONE device-to-host copy in the common case: the header and the first spec_keys keys
+    const uint64_t max_keys = (ob - sl.out_keys) / 8;
+    sl.spec_keys = std::min<uint64_t>(max_keys, std::max<uint64_t>(8192, 8ull * n_main));
+    sl.h_out.ensure(sl.out_keys + sl.spec_keys * 8);
+    CK(cudaStreamWaitEvent(ix->s_out, sl.ev_main, 0));
+    {
+        PhaseScope ps(ix, PH_D2H, ix->s_out);
+        CK(cudaMemcpyAsync(sl.h_out.p, sl.d_out.p, sl.out_keys + sl.spec_keys * 8, cudaMemcpyDeviceToHost,
+                           ix->s_out));
+    }
+    CK(cudaEventRecord(sl.ev(sl.ev_out), ix->s_out));
+    return sl;
+}
+
+// Waits for a submitted batch and assembles its result lists (query order) in the slot.
+void collect_batch(cobsgpu_index* ix, Slot& sl) {
+    if (!sl.busy) throw Err{ COBSGPU_ERR_INVALID_ARG, "ticket is not in flight" };
+    struct Release {
+        Slot& sl;
+        ~Release() { sl.busy = false; }
+    } release{ sl };
+    CK(cudaEventSynchronize(sl.ev_out));
+    const uint32_t nq = sl.nq;
+    const int* flags = sl.h_out.as<int>();
+    if (flags[0] != FLAG_CLEAR) throw_bad_base(sl.q0 + static_cast<uint32_t>(flags[0]));
+    sl.r_off.assign(1, 0);
+    sl.r_doc.clear();
+    sl.r_score.clear();
+
     std::vector<HostList> lists;
     std::vector<std::pair<uint32_t, uint32_t>> where(nq, { 0u, 0u });   // query -> (list, slot)
-    bool identity_single = false;
-
-    if (!short_ids.empty()) {
-        if (threshold <= 0.0) {
-            // every document passes: go straight to the exhaustive path
-            run_exhaustive(ix, short_ids, false, limit, &lists, &where, st);
+    std::vector<uint32_t> redo = sl.huge_ids;
+    const bool all_main = sl.huge_ids.empty();
+    if (sl.mode < 0) {
+        if (all_main) {
+            redo.resize(nq);
+            for (uint32_t i = 0; i < nq; ++i) redo[i] = i;
         } else {
-            const bool identity = long_ids.empty();
-            const uint32_t* d_ql =
-                identity ? nullptr : upload_qlist(ix, short_ids, 0, short_ids.size(), st);
-            const uint32_t n = static_cast<uint32_t>(short_ids.size());
-            const uint32_t cap = std::min<uint32_t>(ix->max_candidates, std::max<uint32_t>(ix->shard_real_docs, 1));
-            bool lis = false;
-            run_pass(ix, d_ql, n, cap, false, 255, limit, &lis, st);
-            lists.emplace_back();
-            std::vector<uint32_t> counts;
-            fetch_pass(ix, d_ql, n, cap, lis, &lists.back(), &counts, st);
-            std::vector<uint32_t> over;
-            for (uint32_t i = 0; i < n; ++i) {
-                where[short_ids[i]] = { 0u, i };
-                if (counts[i] > cap) over.push_back(short_ids[i]);
-            }
-            // queries with more candidates than slots are redone exhaustively: nothing is
-            // ever dropped silently
-            run_exhaustive(ix, over, false, limit, &lists, &where, st);
-            identity_single = identity && over.empty();
+            redo.insert(redo.end(), sl.main_ids.begin(), sl.main_ids.end());
+            std::sort(redo.begin(), redo.end());
+        }
+    } else {
+        const uint32_t n_main = all_main ? nq : static_cast<uint32_t>(sl.main_ids.size());
+        const char* h = sl.h_out.as<char>();
+        const uint64_t* off = reinterpret_cast<const uint64_t*>(h + sl.out_off);
+        const uint32_t* cc = reinterpret_cast<const uint32_t*>(h + sl.out_cc);
+        const uint64_t total = off[n_main];
+        if (total > sl.spec_keys) {
+            // more results than the speculative copy carried: fetch the rest
+            sl.h_out.ensure_keep(sl.out_keys + total * 8, sl.out_keys + sl.spec_keys * 8);
+            h = sl.h_out.as<char>();
+            off = reinterpret_cast<const uint64_t*>(h + sl.out_off);
+            cc = reinterpret_cast<const uint32_t*>(h + sl.out_cc);
+            PhaseScope ps(ix, PH_D2H, ix->s_out);
+            CK(cudaMemcpyAsync(sl.h_out.as<char>() + sl.out_keys + sl.spec_keys * 8,
+                               sl.o_keys() + sl.spec_keys, (total - sl.spec_keys) * 8,
+                               cudaMemcpyDeviceToHost, ix->s_out));
+            CK(cudaStreamSynchronize(ix->s_out));
+        }
+        lists.emplace_back();
+        HostList& L = lists.back();
+        L.off.assign(off, off + n_main + 1);
+        L.doc.resize(total);
+        L.score.resize(total);
+        decode_keys(reinterpret_cast<const uint64_t*>(h + sl.out_keys), total, L.doc.data(), L.score.data());
+        for (uint32_t i = 0; i < n_main; ++i) {
+            const uint32_t q = all_main ? i : sl.main_ids[i];
+            where[q] = { 0u, i };
+            // more candidates than slots: redone exhaustively, nothing is ever dropped silently
+            if (cc[i] > sl.cap) redo.push_back(q);
+        }
+        if (redo.empty() && all_main) {
+            // the common case: the pass's CSR is the batch's result
+            sl.r_off.swap(L.off);
+            sl.r_doc.swap(L.doc);
+            sl.r_score.swap(L.score);
+            return;
         }
     }
-    run_exhaustive(ix, long_ids, true, limit, &lists, &where, st);
-    check_bad_base(ix, q0, st);
-
-    // append to the call's result in query order
-    const uint64_t base = ix->r_off.back();
-    if (identity_single) {
-        const HostList& L = lists[0];
-        for (uint32_t i = 0; i < nq; ++i) ix->r_off.push_back(base + L.off[i + 1]);
-        ix->r_doc.insert(ix->r_doc.end(), L.doc.begin(), L.doc.end());
-        ix->r_score.insert(ix->r_score.end(), L.score.begin(), L.score.end());
-        return;
-    }
-    uint64_t run = base;
+    run_exhaustive(ix, sl, redo, sl.limit, &lists, &where);
+    uint64_t run = 0;
     for (uint32_t i = 0; i < nq; ++i) {
-        if (!lists.empty()) {
-            const HostList& L = lists[where[i].first];
-            const uint32_t s = where[i].second;
-            const uint64_t a = L.off[s], b = L.off[s + 1];
-            ix->r_doc.insert(ix->r_doc.end(), L.doc.begin() + a, L.doc.begin() + b);
-            ix->r_score.insert(ix->r_score.end(), L.score.begin() + a, L.score.begin() + b);
-            run += b - a;
-        }
-        ix->r_off.push_back(run);
+        const HostList& L = lists[where[i].first];
+        const uint32_t s = where[i].second;
+        const uint64_t a = L.off[s], b = L.off[s + 1];
+        sl.r_doc.insert(sl.r_doc.end(), L.doc.begin() + a, L.doc.begin() + b);
+        sl.r_score.insert(sl.r_score.end(), L.score.begin() + a, L.score.begin() + b);
+        run += b - a;
+        sl.r_off.push_back(run);
     }
 }
 
-// batch boundaries: at most max_batch queries and a bounded number of k-mers
-uint32_t next_batch_end(const cobsgpu_index* ix, const uint64_t* offsets, uint32_t q0, uint32_t nq) {
+// batch boundaries: at most max_batch queries, a bounded number of k-mers, and candidate
+// buffers that fit the workspace
+uint32_t next_batch_end(const cobsgpu_index* ix, const uint64_t* offsets, uint32_t q0, uint32_t nq,
+                        uint64_t limit) {
     const uint64_t kmer_budget = 64ull << 20;
+    uint64_t max_q = ix->max_batch;
+    if (limit >= 1 && limit <= TOPK_MAX_K) {
+        const uint64_t cap = std::max<uint64_t>(1, static_cast<uint64_t>(ix->warps_per_query) * limit);
+        max_q = std::max<uint64_t>(1, std::min<uint64_t>(max_q, ix->workspace_bytes / (cap * 8)));
+    }
     uint64_t kmers = 0;
     uint32_t q = q0;
-    while (q < nq && q - q0 < ix->max_batch) {
+    while (q < nq && q - q0 < max_q) {
         const uint64_t len = offsets[q + 1] - offsets[q];
         const uint64_t T = len >= ix->term_size ? len - ix->term_size + 1 : 0;
         if (q > q0 && kmers + T > kmer_budget) break;
@@ -1010,6 +1248,18 @@ uint32_t next_batch_end(const cobsgpu_index* ix, const uint64_t* offsets, uint32
         ++q;
     }
     return q;
+}
+
+void check_idle(const cobsgpu_index* ix) {
+    for (const Slot& sl : ix->slots)
+        if (sl.busy)
+            throw Err{ COBSGPU_ERR_INVALID_ARG, "batches are in flight: collect every ticket first" };
+}
+
+void drop_tickets(cobsgpu_index* ix) {
+    for (cudaStream_t st : { ix->s_in, ix->stream, ix->s_out })
+        if (st) cudaStreamSynchronize(st);
+    for (Slot& sl : ix->slots) sl.busy = false;
 }
 
 }  // namespace
@@ -1312,13 +1562,19 @@ int cobsgpu_hash(cobsgpu_index* ix, const char* queries, const uint64_t* offsets
     return guarded([&] {
         if (!ix || !offsets || (!queries && nq)) throw Err{ COBSGPU_ERR_INVALID_ARG, "null argument" };
         CK(cudaSetDevice(ix->device));
+        check_idle(ix);
+        Slot& sl = ix->aux;
+        cudaStream_t st = ix->stream;
         uint64_t done = 0;
         for (uint32_t q0 = 0; q0 < nq;) {
-            const uint32_t q1 = next_batch_end(ix, offsets, q0, nq);
-            prepare_batch(ix, queries, false, offsets, q0, q1, 0.0, ix->stream);
-            const uint64_t n = static_cast<uint64_t>(ix->b_total_kmers) * ix->num_hashes;
-            CK(cudaMemcpyAsync(out + done, ix->hashes().p, n * 8, cudaMemcpyDeviceToHost, ix->stream));
-            check_bad_base(ix, q0, ix->stream);
+            const uint32_t q1 = next_batch_end(ix, offsets, q0, nq, 0);
+            prepare_batch(ix, sl, queries, false, offsets, q0, q1, 0.0, st);
+            const uint64_t n = static_cast<uint64_t>(sl.total_kmers) * ix->num_hashes;
+            int flags[2];
+            CK(cudaMemcpyAsync(out + done, sl.d_hashes.p, n * 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(flags, sl.d_flags(), sizeof(flags), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (flags[0] != FLAG_CLEAR) throw_bad_base(q0 + static_cast<uint32_t>(flags[0]));
             done += n;
             q0 = q1;
         }
@@ -1331,30 +1587,32 @@ int cobsgpu_scores(cobsgpu_index* ix, const char* queries, const uint64_t* offse
     return guarded([&] {
         if (!ix || !offsets || (!queries && nq) || !out) throw Err{ COBSGPU_ERR_INVALID_ARG, "null argument" };
         CK(cudaSetDevice(ix->device));
+        check_idle(ix);
+        Slot& sl = ix->aux;
         cudaStream_t st = ix->stream;
         const uint64_t counts_size = 8 * ix->page_size_src * ix->n_pages_global;
         for (uint32_t q0 = 0; q0 < nq;) {
-            const uint32_t q1 = next_batch_end(ix, offsets, q0, nq);
-            prepare_batch(ix, queries, false, offsets, q0, q1, 0.0, st);
+            const uint32_t q1 = next_batch_end(ix, offsets, q0, nq, 0);
+            prepare_batch(ix, sl, queries, false, offsets, q0, q1, 0.0, st);
             std::vector<uint32_t> ids[2];   // [0] short (u8 planes suffice), [1] long
             for (uint32_t i = 0; i < q1 - q0; ++i)
-                ids[ix->b_koff[i + 1] - ix->b_koff[i] > 255 ? 1 : 0].push_back(i);
+                ids[sl.koff[i + 1] - sl.koff[i] > MAX_T_SHORT ? 1 : 0].push_back(i);
             for (int lm = 0; lm < 2; ++lm) {
                 const size_t esz = lm ? 4 : 1;
                 const size_t sub = static_cast<size_t>(std::max<uint64_t>(
                     1, std::min<uint64_t>(ids[lm].size(), ix->workspace_bytes / (ix->dense_pitch * esz))));
                 for (size_t b = 0; b < ids[lm].size(); b += sub) {
                     const size_t n = std::min(sub, ids[lm].size() - b);
-                    const uint32_t* d_ql = upload_qlist(ix, ids[lm], b, n, st);
+                    const uint32_t* d_ql = upload_qlist(sl, ids[lm], b, n, st);
                     const size_t bytes = n * ix->dense_pitch * esz;
-                    ix->d_dense.ensure(bytes);
-                    CK(cudaMemsetAsync(ix->d_dense.p, 0, bytes, st));
-                    ScoreParams sp = base_params(ix, d_ql, static_cast<uint32_t>(n));
-                    sp.dense8 = ix->d_dense.as<uint8_t>();
-                    sp.dense32 = ix->d_dense.as<uint32_t>();
-                    launch_score(ix, sp, lm ? MODE_DENSE32 : MODE_DENSE8, st);
-                    ix->h_dense.ensure(bytes);
-                    CK(cudaMemcpyAsync(ix->h_dense.p, ix->d_dense.p, bytes, cudaMemcpyDeviceToHost, st));
+                    sl.d_dense.ensure(bytes);
+                    CK(cudaMemsetAsync(sl.d_dense.p, 0, bytes, st));
+                    ScoreParams sp = base_params(ix, sl, d_ql, static_cast<uint32_t>(n));
+                    sp.dense8 = sl.d_dense.as<uint8_t>();
+                    sp.dense32 = sl.d_dense.as<uint32_t>();
+                    launch_score(ix, sp, lm ? MODE_DENSE32 : MODE_DENSE8, false, st);
+                    sl.h_out.ensure(bytes);
+                    CK(cudaMemcpyAsync(sl.h_out.p, sl.d_dense.p, bytes, cudaMemcpyDeviceToHost, st));
                     CK(cudaStreamSynchronize(st));
                     // shard-local dense layout -> the reference's score_list layout
                     for (size_t i = 0; i < n; ++i) {
@@ -1364,17 +1622,20 @@ int cobsgpu_scores(cobsgpu_index* ix, const char* queries, const uint64_t* offse
                                                   8 * lp.byte_begin;
                             const uint64_t cols = static_cast<uint64_t>(lp.row_bytes) * 8;
                             if (lm) {
-                                const uint32_t* s = ix->h_dense.as<uint32_t>() + i * ix->dense_pitch + lp.dense_off;
+                                const uint32_t* s = sl.h_out.as<uint32_t>() + i * ix->dense_pitch + lp.dense_off;
                                 std::memcpy(dst + gcol, s, cols * 4);
                             } else {
-                                const uint8_t* s = ix->h_dense.as<uint8_t>() + i * ix->dense_pitch + lp.dense_off;
+                                const uint8_t* s = sl.h_out.as<uint8_t>() + i * ix->dense_pitch + lp.dense_off;
                                 for (uint64_t c = 0; c < cols; ++c) dst[gcol + c] = s[c];
                             }
                         }
                     }
                 }
             }
-            check_bad_base(ix, q0, st);
+            int flags[2];
+            CK(cudaMemcpyAsync(flags, sl.d_flags(), sizeof(flags), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (flags[0] != FLAG_CLEAR) throw_bad_base(q0 + static_cast<uint32_t>(flags[0]));
             q0 = q1;
         }
         resolve_timers(ix);
@@ -1387,18 +1648,87 @@ int cobsgpu_search_batch(cobsgpu_index* ix, const char* queries, const uint64_t*
     return guarded([&] {
         if (!ix || !offsets || (!queries && nq) || !out) throw Err{ COBSGPU_ERR_INVALID_ARG, "null argument" };
         CK(cudaSetDevice(ix->device));
+        check_idle(ix);
         ix->r_off.assign(1, 0);
         ix->r_doc.clear();
         ix->r_score.clear();
-        for (uint32_t q0 = 0; q0 < nq;) {
-            const uint32_t q1 = next_batch_end(ix, offsets, q0, nq);
-            search_one_batch(ix, queries, offsets, q0, q1, threshold, num_results);
-            q0 = q1;
+        // sub-batches are pipelined through the slot ring: up to N_SLOTS - 1 in flight
+        std::vector<Slot*> inflight;
+        size_t head = 0, n_batches = 0;
+        Slot* last = nullptr;
+        auto drain_one = [&] {
+            Slot& sl = *inflight[head++];
+            collect_batch(ix, sl);
+            last = &sl;
+            if (++n_batches == 1 && head == inflight.size()) return;   // maybe the only batch
+            if (n_batches == 2) {
+                // first batch was left in its slot: move it over now
+                Slot& f = *inflight[0];
+                ix->r_off.insert(ix->r_off.end(), f.r_off.begin() + 1, f.r_off.end());
+                ix->r_doc = f.r_doc;
+                ix->r_score = f.r_score;
+            }
+            if (n_batches >= 2) {
+                const uint64_t base = ix->r_off.back();
+                for (size_t i = 1; i < sl.r_off.size(); ++i) ix->r_off.push_back(base + sl.r_off[i]);
+                ix->r_doc.insert(ix->r_doc.end(), sl.r_doc.begin(), sl.r_doc.end());
+                ix->r_score.insert(ix->r_score.end(), sl.r_score.begin(), sl.r_score.end());
+            }
+        };
+        try {
+            for (uint32_t q0 = 0; q0 < nq;) {
+                const uint32_t q1 = next_batch_end(ix, offsets, q0, nq, num_results);
+                if (inflight.size() - head == cobsgpu_index::N_SLOTS - 1) drain_one();
+                inflight.push_back(&submit_batch(ix, queries, offsets, q0, q1, threshold, num_results));
+                q0 = q1;
+            }
+            while (head < inflight.size()) drain_one();
+        } catch (...) {
+            drop_tickets(ix);
+            throw;
         }
         resolve_timers(ix);
+        if (n_batches == 1) {
+            // single batch: hand out the slot's own arrays (valid until the next call)
+            out->offsets = last->r_off.data();
+            out->doc = last->r_doc.data();
+            out->score = last->r_score.data();
+            return;
+        }
         out->offsets = ix->r_off.data();
         out->doc = ix->r_doc.data();
         out->score = ix->r_score.data();
+    });
+}
+
+int cobsgpu_submit(cobsgpu_index* ix, const char* queries, const uint64_t* offsets, uint32_t nq,
+                   double threshold, uint64_t num_results, cobsgpu_ticket* ticket) {
+    return guarded([&] {
+        if (!ix || !offsets || (!queries && nq) || !ticket) throw Err{ COBSGPU_ERR_INVALID_ARG, "null argument" };
+        if (nq == 0) throw Err{ COBSGPU_ERR_INVALID_ARG, "empty batch" };
+        CK(cudaSetDevice(ix->device));
+        if (next_batch_end(ix, offsets, 0, nq, num_results) != nq)
+            throw Err{ COBSGPU_ERR_INVALID_ARG,
+                       "batch too large for one ticket (see the max_batch / workspace_mb options)" };
+        Slot& sl = submit_batch(ix, queries, offsets, 0, nq, threshold, num_results);
+        *ticket = sl.ticket;
+    });
+}
+
+int cobsgpu_collect(cobsgpu_index* ix, cobsgpu_ticket ticket, cobsgpu_result* out) {
+    return guarded([&] {
+        if (!ix || !out) throw Err{ COBSGPU_ERR_INVALID_ARG, "null argument" };
+        CK(cudaSetDevice(ix->device));
+        for (Slot& sl : ix->slots) {
+            if (!sl.busy || sl.ticket != ticket) continue;
+            collect_batch(ix, sl);
+            resolve_timers(ix);
+            out->offsets = sl.r_off.data();
+            out->doc = sl.r_doc.data();
+            out->score = sl.r_score.data();
+            return;
+        }
+        throw Err{ COBSGPU_ERR_INVALID_ARG, "unknown ticket" };
     });
 }
 
@@ -1412,82 +1742,47 @@ int cobsgpu_search_batch_device(cobsgpu_index* ix, const char* d_queries, const 
         if (nq == 0) return;
         CK(cudaSetDevice(ix->device));
         cudaStream_t st = static_cast<cudaStream_t>(stream);
-        // "prefetch": metadata upload + K1 run ahead on an internal stream, on the buffer set
-        // the previous call does not use, and only K2/K3 are ordered on the caller's stream
-        int set = -1;
+        Slot& sl = take_slot(ix);
+        // "prefetch": metadata upload + K1 run ahead on s_in, in a slot no earlier call still
+        // reads, and only K2/K3 are ordered on the caller's stream
         cudaStream_t ks = st;
         if (ix->prefetch) {
-            if (!ix->pre_stream) {
-                CK(cudaStreamCreateWithFlags(&ix->pre_stream, cudaStreamNonBlocking));
-                CK(cudaEventCreateWithFlags(&ix->ev_in, cudaEventDisableTiming));
-                for (int i = 0; i < 2; ++i) {
-                    CK(cudaEventCreateWithFlags(&ix->ev_k1[i], cudaEventDisableTiming));
-                    CK(cudaEventCreateWithFlags(&ix->ev_k2[i], cudaEventDisableTiming));
-                }
-            }
-            ix->cur ^= 1;
-            set = ix->cur;
-            ks = ix->pre_stream;
+            ks = ix->s_in;
             if (!ix->inputs_ready) {   // d_queries may still be produced on the caller's stream
-                CK(cudaEventRecord(ix->ev_in, st));
-                CK(cudaStreamWaitEvent(ks, ix->ev_in, 0));
+                if (!ix->ev_caller) CK(cudaEventCreateWithFlags(&ix->ev_caller, cudaEventDisableTiming));
+                CK(cudaEventRecord(ix->ev_caller, st));
+                CK(cudaStreamWaitEvent(ks, ix->ev_caller, 0));
             }
-            if (ix->ev_k2_valid[set]) CK(cudaStreamWaitEvent(ks, ix->ev_k2[set], 0));
+            // the slot's previous K2/K3 (N_SLOTS calls ago) must have finished with its buffers
+            if (sl.ev_main) CK(cudaStreamWaitEvent(ks, sl.ev_main, 0));
         }
-        prepare_batch(ix, d_queries, true, offsets, 0, nq, threshold, ks);
-        if (set >= 0) {
-            CK(cudaEventRecord(ix->ev_k1[set], ks));
-            CK(cudaStreamWaitEvent(st, ix->ev_k1[set], 0));
+        prepare_batch(ix, sl, d_queries, true, offsets, 0, nq, threshold, ks);
+        if (ks != st) {
+            CK(cudaEventRecord(sl.ev(sl.ev_in), ks));
+            CK(cudaStreamWaitEvent(st, sl.ev_in, 0));
         }
-        struct K2Done {   // marks the buffer set free once K2/K3 of this call are enqueued
-            cobsgpu_index* ix;
-            int set;
+        struct MainDone {   // marks the slot's buffers free once K2/K3 of this call are enqueued
+            Slot& sl;
             cudaStream_t st;
-            ~K2Done() {
-                if (set >= 0 && cudaEventRecord(ix->ev_k2[set], st) == cudaSuccess)
-                    ix->ev_k2_valid[set] = true;
-            }
-        } k2done{ ix, set, st };
-        for (uint32_t i = 0; i < nq; ++i)
-            if (ix->b_koff[i + 1] - ix->b_koff[i] > 255)
-                throw Err{ COBSGPU_ERR_INVALID_ARG,
-                           "device-resident path handles queries of at most 255 k-mers" };
-        const uint32_t cap = std::max<uint32_t>(results_per_query, ix->max_candidates);
-        if (cap <= SORT_SMALL_MAX) {
-            // fused K3: count + sort + strided output in one launch
-            ix->d_cand.ensure(static_cast<uint64_t>(nq) * cap * 8);
-            ix->d_cand_count.ensure(nq * 4);
-            CK(cudaMemsetAsync(ix->d_cand_count.p, 0, nq * 4, st));
-            ScoreParams sp = base_params(ix, nullptr, nq);
-            sp.cand_count = ix->d_cand_count.as<uint32_t>();
-            sp.cand = ix->d_cand.as<uint64_t>();
-            sp.cap = cap;
-            launch_score(ix, sp, MODE_CAND, st);
-            PhaseScope ps(ix, PH_SELECT, st);
-            FinalizeParams fp{ sp.cand, sp.cand_count, ix->d_bad(), cap, nq, num_results, d_keys,
-                               d_counts, results_per_query };
-            finalize_strided_kernel<<<div_ceil<uint32_t>(nq, FIN_WARPS), FIN_WARPS * 32, 0, st>>>(fp);
-            CK(cudaGetLastError());
-            ix->tm.kernel_launches++;
-            return;
+            ~MainDone() { cudaEventRecord(sl.ev(sl.ev_main), st); }
+        } main_done{ sl, st };
+        if (sl.max_T > MAX_T_LONG)
+            throw Err{ COBSGPU_ERR_INVALID_ARG,
+                       "device-resident path handles queries of at most 65535 k-mers" };
+        PassPlan pl;
+        if (!plan_main_pass(ix, sl, threshold, num_results, sl.max_T, &pl) || pl.mode == MODE_CAND) {
+            // (threshold <= 0 without a small limit: every query overflows and is flagged)
+            pl.mode = MODE_CAND;
+            pl.lng = sl.max_T > MAX_T_SHORT;
+            pl.limit = num_results;
+            pl.cap = std::min<uint32_t>(std::max<uint32_t>(results_per_query, ix->max_candidates),
+                                        std::max<uint32_t>(ix->shard_real_docs, 1));
         }
-        bool lis = false;
-        run_pass(ix, nullptr, nq, cap, false, 255, num_results, &lis, st);
-        PhaseScope ps(ix, PH_SELECT, st);
-        GatherParams gp{};
-        gp.cand = ix->d_cand.as<uint64_t>();
-        gp.scratch = ix->d_scratch.as<uint64_t>();
-        gp.cand_count = ix->d_cand_count.as<uint32_t>();
-        gp.res_count = ix->d_res_count.as<uint32_t>();
-        gp.cap = cap;
-        gp.large_in_scratch = lis ? 1 : 0;
-        gp.out_keys = d_keys;
-        gp.out_counts = d_counts;
-        gp.bad = ix->d_bad();
-        gp.stride = results_per_query;
-        gather_kernel<<<nq, 256, 0, st>>>(gp);
-        CK(cudaGetLastError());
-        ix->tm.kernel_launches++;
+        sl.layout_out(nq);
+        sl.d_out.ensure(sl.out_keys);
+        launch_pass_score(ix, sl, sl, nullptr, nq, pl, sl.o_cc(), st);
+        launch_select(ix, sl, sl, nullptr, nq, pl, sl.max_T, sl.o_cc(), d_keys, d_counts,
+                      results_per_query, true, st);
     });
 }
 

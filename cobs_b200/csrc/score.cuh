@@ -25,15 +25,23 @@
 //   * epilogue per item: CAND  -> bit-sliced compare against ceil(threshold*T), survivors are
 //                                 appended (warp-aggregated atomics) as sort keys;
 //                         DENSE8 -> the 128 counts are transposed out of the planes and stored;
-//                         DENSE32-> counts are added into a u32 score vector every 248 k-mers
-//                                   (queries with more than 255 k-mers).
+//                         DENSE32-> counts are added into a u32 score vector (flushed before the
+//                                   planes could overflow; any query length);
+//                         TOPK  -> every consumer warp keeps only the best `topk` of its 4096
+//                                  documents under the reference's order (score desc, doc asc):
+//                                  a bit-sliced binary search for the cutoff score plus a
+//                                  prefix-limited tie mask.  The union of the per-warp lists
+//                                  contains the query's global top-k, never overflows, and is
+//                                  tiny, so `-t 0 -l k` no longer materialises every document.
+//   * NP = number of bit-planes per word: 8 (queries of <= 255 k-mers) or 16 (<= 65 535).
 #pragma once
 
 #include "common.cuh"
 
 namespace cobsgpu {
 
-enum ScoreMode : int { MODE_CAND = 0, MODE_DENSE8 = 1, MODE_DENSE32 = 2 };
+enum ScoreMode : int { MODE_CAND = 0, MODE_DENSE8 = 1, MODE_DENSE32 = 2, MODE_TOPK = 3 };
+static constexpr int SCORE_MODES = 4;
 
 // one column tile of one page of the shard held by this device
 struct TileDesc {
@@ -61,6 +69,7 @@ struct ScoreParams {
     uint32_t* cand_count;     // [nq_items]
     uint64_t* cand;           // [nq_items * cap]
     uint32_t cap;
+    uint32_t topk;            // MODE_TOPK: results wanted per query (>= 1)
     // MODE_DENSE8 / MODE_DENSE32
     uint8_t* dense8;          // [nq_items * dense_pitch]
     uint32_t* dense32;        // [nq_items * dense_pitch] (zero-initialised)
@@ -77,7 +86,8 @@ __host__ __device__ constexpr uint32_t score_smem_header(uint32_t ns) {
 static constexpr uint32_t SCORE_ITEM_Q = 2;   // item ids the producer may run ahead
 
 static constexpr int SCORE_MAX_THREADS = 160;   // 4 consumer warps + 1 producer warp
-static constexpr int SCORE_PLANES = 8;          // counts up to 255 between flushes
+static constexpr int SCORE_PLANES = 8;          // short queries: counts up to 255
+static constexpr int SCORE_PLANES_LONG = 16;    // long queries: counts up to 65 535
 
 // full adder over 32 lanes of documents
 #define COBS_CSA(sum, carry, a, b, c)            \
@@ -89,12 +99,13 @@ static constexpr int SCORE_PLANES = 8;          // counts up to 255 between flus
     }
 
 // documents of a 32-bit word whose bit-sliced count is >= thr
-__host__ __device__ __forceinline__ uint32_t planes_ge(const uint32_t (&pl)[SCORE_PLANES], uint32_t thr) {
+template <int NP>
+__host__ __device__ __forceinline__ uint32_t planes_ge(const uint32_t (&pl)[NP], uint32_t thr) {
     if (thr == 0) return 0xFFFFFFFFu;
-    if (thr > 255) return 0u;
+    if ((thr >> NP) != 0) return 0u;
     uint32_t gt = 0, eq = 0xFFFFFFFFu;
 #pragma unroll
-    for (int i = SCORE_PLANES - 1; i >= 0; --i) {
+    for (int i = NP - 1; i >= 0; --i) {
         if ((thr >> i) & 1u) {
             eq &= pl[i];
         } else {
@@ -105,26 +116,33 @@ __host__ __device__ __forceinline__ uint32_t planes_ge(const uint32_t (&pl)[SCOR
     return gt | eq;
 }
 
-__host__ __device__ __forceinline__ uint32_t planes_count(const uint32_t (&pl)[SCORE_PLANES], uint32_t bit) {
+template <int NP>
+__host__ __device__ __forceinline__ uint32_t planes_count(const uint32_t (&pl)[NP], uint32_t bit) {
     uint32_t c = 0;
 #pragma unroll
-    for (int i = 0; i < SCORE_PLANES; ++i) c |= ((pl[i] >> bit) & 1u) << i;
+    for (int i = 0; i < NP; ++i) c |= ((pl[i] >> bit) & 1u) << i;
     return c;
 }
 
-// counts of documents 4g..4g+3 of a word, one per byte (8x4 bit-matrix transpose by multiply)
-__host__ __device__ __forceinline__ uint32_t planes_pack4(const uint32_t (&pl)[SCORE_PLANES], uint32_t g) {
+// bits [8*B, 8*B+8) of the counts of documents 4g..4g+3 of a word, one per byte (8x4 bit-matrix
+// transpose by multiply)
+template <int B = 0, int NP>
+__host__ __device__ __forceinline__ uint32_t planes_pack4(const uint32_t (&pl)[NP], uint32_t g) {
+    static_assert(8 * B + 8 <= NP, "plane byte out of range");
     uint32_t out = 0;
 #pragma unroll
-    for (int i = 0; i < SCORE_PLANES; ++i) {
-        uint32_t nib = (pl[i] >> (4 * g)) & 0xFu;
+    for (int i = 0; i < 8; ++i) {
+        uint32_t nib = (pl[8 * B + i] >> (4 * g)) & 0xFu;
         out |= ((nib * 0x00204081u) & 0x01010101u) << i;
     }
     return out;
 }
 
-template <int H, int MODE>
+template <int H, int MODE, int NP>
 __global__ void __launch_bounds__(SCORE_MAX_THREADS, 3) score_kernel(const ScoreParams p) {
+    static_assert(NP == SCORE_PLANES || NP == SCORE_PLANES_LONG, "8 or 16 bit-planes");
+    static_assert(MODE != MODE_DENSE8 || NP == 8, "DENSE8 stores one byte per document");
+    constexpr uint32_t MAXC = (1u << NP) - 1u;   // largest count the planes can hold
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t h = H > 0 ? static_cast<uint32_t>(H) : p.h;
     const uint32_t ncw = (blockDim.x >> 5) - 1;   // consumer warps; the last warp produces
@@ -238,11 +256,11 @@ __global__ void __launch_bounds__(SCORE_MAX_THREADS, 3) score_kernel(const Score
         const uint32_t T = p.koff[q + 1] - p.koff[q];
         const bool active = threadIdx.x * 16 < td.bytes;
 
-        uint32_t pl[4][SCORE_PLANES];
+        uint32_t pl[4][NP];
 #pragma unroll
         for (int w = 0; w < 4; ++w)
 #pragma unroll
-            for (int i = 0; i < SCORE_PLANES; ++i) pl[w][i] = 0;
+            for (int i = 0; i < NP; ++i) pl[w][i] = 0;
 
         // AND of the h row slices of the next k-mer, 128 documents per thread
         auto fetch = [&](uint32_t (&x)[4]) {
@@ -300,11 +318,13 @@ __global__ void __launch_bounds__(SCORE_MAX_THREADS, 3) score_kernel(const Score
 #pragma unroll
                     for (int g = 0; g < 8; ++g) {
                         const uint32_t pk = planes_pack4(pl[w], g);
+                        uint32_t ph = 0;   // (DENSE32 is instantiated with 8 planes: ph stays 0)
+                        if (NP > 8) ph = planes_pack4<(NP > 8 ? 1 : 0)>(pl[w], g);
                         uint4 a = dst[8 * w + g];
-                        a.x += pk & 0xFFu;
-                        a.y += (pk >> 8) & 0xFFu;
-                        a.z += (pk >> 16) & 0xFFu;
-                        a.w += pk >> 24;
+                        a.x += (pk & 0xFFu) | ((ph & 0xFFu) << 8);
+                        a.y += ((pk >> 8) & 0xFFu) | (((ph >> 8) & 0xFFu) << 8);
+                        a.z += ((pk >> 16) & 0xFFu) | (((ph >> 16) & 0xFFu) << 8);
+                        a.w += (pk >> 24) | ((ph >> 24) << 8);
                         dst[8 * w + g] = a;
                     }
                 }
@@ -314,14 +334,14 @@ __global__ void __launch_bounds__(SCORE_MAX_THREADS, 3) score_kernel(const Score
 #pragma unroll
             for (int w = 0; w < 4; ++w)
 #pragma unroll
-                for (int i = 0; i < SCORE_PLANES; ++i) pl[w][i] = 0;
+                for (int i = 0; i < NP; ++i) pl[w][i] = 0;
         };
 
         uint32_t t = 0, acc = 0;   // acc = k-mers held in the planes since the last flush
         // groups of 8 k-mers through a carry-save adder tree: planes 0..2 are the tree's
-        // ones/twos/fours, the carry of weight 8 ripples into planes 3..7
+        // ones/twos/fours, the carry of weight 8 ripples into planes 3..NP-1
         for (; t + 8 <= T; t += 8) {
-            if (MODE == MODE_DENSE32 && acc + 8 > 255) {
+            if (MODE == MODE_DENSE32 && acc + 8 > MAXC) {
                 flush_dense();
                 clear_planes();
                 acc = 0;
@@ -351,17 +371,26 @@ __global__ void __launch_bounds__(SCORE_MAX_THREADS, 3) score_kernel(const Score
                 COBS_CSA(pl[w][1], t4b[w], pl[w][1], t2a[w], t2b[w]);
                 COBS_CSA(pl[w][2], t8, pl[w][2], t4a[w], t4b[w]);
 #pragma unroll
-                for (int i = 3; i < SCORE_PLANES; ++i) {
+                for (int i = 3; i < 8; ++i) {
                     const uint32_t n = pl[w][i] & t8;
                     pl[w][i] ^= t8;
                     t8 = n;
+                }
+                // planes 8..15 only see a carry when a count crosses a multiple of 256: rare
+                if (NP > 8 && t8 != 0) {
+#pragma unroll
+                    for (int i = 8; i < NP; ++i) {
+                        const uint32_t n = pl[w][i] & t8;
+                        pl[w][i] ^= t8;
+                        t8 = n;
+                    }
                 }
             }
             acc += 8;
         }
         // tail (< 8 k-mers): plain ripple-carry increment
         for (; t < T; ++t) {
-            if (MODE == MODE_DENSE32 && acc + 1 > 255) {
+            if (MODE == MODE_DENSE32 && acc + 1 > MAXC) {
                 flush_dense();
                 clear_planes();
                 acc = 0;
@@ -372,7 +401,7 @@ __global__ void __launch_bounds__(SCORE_MAX_THREADS, 3) score_kernel(const Score
             for (int w = 0; w < 4; ++w) {
                 uint32_t c = x[w];
 #pragma unroll
-                for (int i = 0; i < SCORE_PLANES; ++i) {
+                for (int i = 0; i < NP; ++i) {
                     const uint32_t n = pl[w][i] & c;
                     pl[w][i] ^= c;
                     c = n;
@@ -386,14 +415,78 @@ __global__ void __launch_bounds__(SCORE_MAX_THREADS, 3) score_kernel(const Score
         } else {
             // threshold in bit-sliced form, then append the survivors as sort keys
             const uint32_t thr = p.thr[q];
-            uint32_t m[4], cnt = 0;
+            uint32_t m[4], valid[4], cnt = 0;
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
                 const uint32_t d0 = threadIdx.x * 128 + w * 32;   // first document of the word
                 const uint32_t n = td.n_real > d0 ? td.n_real - d0 : 0;   // real ones (no padding)
-                const uint32_t valid = n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u);
-                m[w] = active ? (planes_ge(pl[w], thr) & valid) : 0u;
-                cnt += __popc(m[w]);
+                valid[w] = !active ? 0u : (n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u));
+            }
+            if (MODE == MODE_TOPK) {
+                // Per-warp top-k under (score desc, doc asc).  Documents of a warp are ordered
+                // (lane, word, bit) == ascending id.  count_ge(t) = documents of this warp with
+                // score >= t; the cutoff c is the largest t >= thr with count_ge(t) >= k: keep
+                // every document above c and the first k - count_ge(c+1) documents equal to c.
+                const uint32_t k = p.topk;
+                auto count_ge = [&](uint32_t t) {
+                    uint32_t c = 0;
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) c += __popc(planes_ge(pl[w], t) & valid[w]);
+                    return __reduce_add_sync(0xFFFFFFFFu, c);
+                };
+                uint32_t lo = thr;
+                if (count_ge(lo) <= k) {
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) m[w] = planes_ge(pl[w], lo) & valid[w];
+                } else {
+                    uint32_t hi = (T < MAXC ? T : MAXC) + 1;   // count_ge(hi) == 0: scores <= T
+                    while (hi - lo > 1) {
+                        const uint32_t mid = lo + ((hi - lo) >> 1);
+                        if (count_ge(mid) >= k) lo = mid;
+                        else hi = mid;
+                    }
+                    uint32_t eq[4], n_gt = 0, n_eq = 0;
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        m[w] = planes_ge(pl[w], lo + 1) & valid[w];
+                        eq[w] = planes_ge(pl[w], lo) & valid[w] & ~m[w];
+                        n_gt += __popc(m[w]);
+                        n_eq += __popc(eq[w]);
+                    }
+                    const uint32_t need = k - __reduce_add_sync(0xFFFFFFFFu, n_gt);   // >= 1
+                    uint32_t pre = n_eq;   // exclusive prefix of the tie counts over the lanes
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, pre, d);
+                        if (lane >= d) pre += o;
+                    }
+                    pre -= n_eq;
+                    uint32_t allow = need > pre ? need - pre : 0;   // ties this lane may keep
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        const uint32_t c = __popc(eq[w]);
+                        if (c > allow) {
+                            uint32_t rest = eq[w], kept = 0;
+                            for (uint32_t i = 0; i < allow; ++i) {
+                                kept |= rest & (0u - rest);
+                                rest &= rest - 1;
+                            }
+                            eq[w] = kept;
+                            allow = 0;
+                        } else {
+                            allow -= c;
+                        }
+                        m[w] |= eq[w];
+                    }
+                }
+#pragma unroll
+                for (int w = 0; w < 4; ++w) cnt += __popc(m[w]);
+            } else {
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    m[w] = planes_ge(pl[w], thr) & valid[w];
+                    cnt += __popc(m[w]);
+                }
             }
             uint32_t incl = cnt;
 #pragma unroll

@@ -11,8 +11,6 @@
 
 namespace cobsgpu {
 
-static constexpr uint32_t SORT_SMALL_MAX = 2048;   // keys sorted in shared memory by one CTA
-static constexpr uint32_t SORT_SMALL_THREADS = 256;
 static constexpr uint32_t SORT_LARGE_THREADS = 1024;
 static constexpr uint32_t MERGE_MAX = 8192;        // keys per query in the shard merge
 // per-query result counts of the device-resident path that flag a query instead of a list
@@ -93,20 +91,6 @@ __global__ void __launch_bounds__(256) dense_to_cand_kernel(DenseToCandParams p)
     }
 }
 
-// n_q = min(cand_count, cap); sets *overflow when a query produced more than cap candidates
-// and results are unbounded (nothing may be dropped silently); result count = min(n_q, limit).
-__global__ void result_counts_kernel(const uint32_t* cand_count, uint32_t nq, uint32_t cap,
-                                     uint64_t limit, uint32_t* res_count, int* overflow) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nq) return;
-    uint32_t c = cand_count[i];
-    if (c > cap) {
-        atomicMin(overflow, static_cast<int>(i));
-        c = cap;
-    }
-    res_count[i] = (limit != 0 && c > limit) ? static_cast<uint32_t>(limit) : c;
-}
-
 // exclusive prefix sum of res_count into 64-bit offsets[nq+1]; single CTA
 __global__ void __launch_bounds__(1024) scan_offsets_kernel(const uint32_t* res_count, uint32_t nq,
                                                             uint64_t* offsets) {
@@ -117,7 +101,8 @@ __global__ void __launch_bounds__(1024) scan_offsets_kernel(const uint32_t* res_
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (uint32_t base = 0; base < nq; base += blockDim.x) {
         const uint32_t i = base + threadIdx.x;
-        const uint64_t v = i < nq ? res_count[i] : 0;
+        uint64_t v = i < nq ? res_count[i] : 0;
+        if (v >= COUNT_INVALID) v = 0;   // flagged query: no list
         uint64_t incl = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -147,23 +132,8 @@ __global__ void __launch_bounds__(1024) scan_offsets_kernel(const uint32_t* res_
     if (threadIdx.x == 0) offsets[nq] = carry;
 }
 
-// one CTA per query: sort the (<= SORT_SMALL_MAX) candidates in shared memory, in place.
-__global__ void __launch_bounds__(SORT_SMALL_THREADS)
-sort_small_kernel(uint64_t* cand, const uint32_t* cand_count, uint32_t cap) {
-    __shared__ uint64_t s[SORT_SMALL_MAX];
-    const uint32_t qi = blockIdx.x;
-    uint32_t n = cand_count[qi];
-    if (n > cap) n = cap;
-    if (n < 2 || n > SORT_SMALL_MAX) return;
-    uint64_t* keys = cand + static_cast<uint64_t>(qi) * cap;
-    const uint32_t np2 = next_pow2(n);
-    for (uint32_t i = threadIdx.x; i < np2; i += blockDim.x) s[i] = i < n ? keys[i] : KEY_PAD;
-    __syncthreads();
-    block_bitonic_sort(s, np2);
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) keys[i] = s[i];
-}
-
-// one CTA per query with more than SORT_SMALL_MAX candidates: LSD radix sort (8-bit digits)
+// one CTA per query with more than `min_n` candidates (what finalize_kernel cannot sort in
+// shared memory): LSD radix sort (8-bit digits)
 // over the varying key bits, ping-ponging between `cand` and `scratch` (same layout).
 // digit_shift[pass] lists the bit offsets to sort on, lowest significance first.
 struct SortLargeParams {
@@ -171,6 +141,7 @@ struct SortLargeParams {
     uint64_t* scratch;
     const uint32_t* cand_count;
     uint32_t cap;
+    uint32_t min_n;        // lists of at most this many keys are left to finalize_kernel
     uint32_t n_pass;
     uint32_t digit_shift[8];
 };
@@ -181,7 +152,7 @@ __global__ void __launch_bounds__(SORT_LARGE_THREADS) sort_large_kernel(SortLarg
     const uint32_t qi = blockIdx.x;
     uint32_t n = p.cand_count[qi];
     if (n > p.cap) n = p.cap;
-    if (n <= SORT_SMALL_MAX) return;
+    if (n <= p.min_n) return;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint64_t* src = p.cand + static_cast<uint64_t>(qi) * p.cap;
     uint64_t* dst = p.scratch + static_cast<uint64_t>(qi) * p.cap;
@@ -255,87 +226,49 @@ __global__ void __launch_bounds__(SORT_LARGE_THREADS) sort_large_kernel(SortLarg
     }
 }
 
-// final formatting.  Sorted keys of slot qi live in `cand` (or in `scratch` when the large
-// sort ran an odd number of passes).  CSR mode: doc/score arrays at offsets[qi];
-// strided mode: keys at out_keys[q * stride] and counts at out_counts[q].
-struct GatherParams {
-    const uint64_t* cand;
-    const uint64_t* scratch;
-    const uint32_t* cand_count;
-    const uint32_t* res_count;
-    const uint32_t* qlist;     // optional: slot -> batch query
-    uint32_t cap;
-    uint32_t large_in_scratch; // 1 if queries with n > SORT_SMALL_MAX ended in scratch
-    // CSR
-    const uint64_t* offsets;   // by batch query
-    uint32_t* out_doc;
-    uint32_t* out_score;
-    // strided
-    uint64_t* out_keys;
-    uint32_t* out_counts;
-    const uint32_t* bad;       // [nq] by batch query, strided mode only
-    uint32_t stride;
-};
-
-__global__ void __launch_bounds__(256) gather_kernel(GatherParams p) {
-    const uint32_t qi = blockIdx.x;
-    const uint32_t q = p.qlist ? p.qlist[qi] : qi;
-    uint32_t n = p.cand_count[qi];
-    if (n > p.cap) n = p.cap;
-    const uint32_t r = p.res_count[qi];
-    const uint64_t* keys = ((n > SORT_SMALL_MAX && p.large_in_scratch) ? p.scratch : p.cand) +
-                           static_cast<uint64_t>(qi) * p.cap;
-    if (p.out_keys) {
-        uint64_t* o = p.out_keys + static_cast<uint64_t>(q) * p.stride;
-        for (uint32_t i = threadIdx.x; i < r && i < p.stride; i += blockDim.x) o[i] = keys[i];
-        // more candidates than slots: the list would be incomplete -> flagged, never silent
-        if (threadIdx.x == 0)
-            p.out_counts[q] = (p.bad && p.bad[q] == 1) ? COUNT_INVALID
-                              : p.cand_count[qi] > p.cap ? COUNT_OVERFLOW
-                                                         : (r < p.stride ? r : p.stride);
-    } else {
-        const uint64_t off = p.offsets[q];
-        for (uint32_t i = threadIdx.x; i < r; i += blockDim.x) {
-            const uint64_t k = keys[i];
-            p.out_doc[off + i] = key_doc(k);
-            p.out_score[off + i] = key_score(k);
-        }
-    }
-}
-
-// Fused K3 for the device-resident path (cap <= SORT_SMALL_MAX): result count + sort + strided
-// output in ONE kernel.  A CTA owns FIN_WARPS queries: lists of <= 32 candidates (the common
-// case at the CLI's default threshold) are sorted by one warp with shuffles; longer ones by the
-// whole CTA in shared memory afterwards.
+// Fused K3: result count + sort + output in ONE kernel.  A CTA owns FIN_WARPS queries: lists of
+// <= 32 candidates (the common case at the CLI's default threshold) are sorted by one warp with
+// shuffles; longer ones (<= FIN_SORT_MAX, dynamic shared memory) by the whole CTA afterwards;
+// lists longer than fin_sort_max were sorted by sort_large_kernel before and are only counted
+// (and copied when the output is not in place).  Output: the first min(n, limit) sorted keys of
+// query q at out_keys[q * stride] (out_keys == cand, stride == cap sorts in place) and
+// out_counts[q] -- or a COUNT_* flag instead of an incomplete list.
 static constexpr uint32_t FIN_WARPS = 8;
+static constexpr uint32_t FIN_SORT_MAX = 8192;   // 64 KB of dynamic shared memory
 
 struct FinalizeParams {
-    const uint64_t* cand;
+    uint64_t* cand;
+    const uint64_t* scratch;   // where sort_large left its result when large_in_scratch
     const uint32_t* cand_count;
-    const uint32_t* bad;    // [nq] == 1: query holds a non-ACGT base (canonicalising index)
+    const uint32_t* bad;       // optional [nq] by batch query, == 1: non-ACGT base (canonical index)
+    const uint32_t* qlist;     // optional: slot -> batch query (only used to look up `bad`)
     uint32_t cap;
     uint32_t nq;
     uint64_t limit;
-    uint64_t* out_keys;     // [nq * stride]
-    uint32_t* out_counts;   // [nq]; COUNT_OVERFLOW / COUNT_INVALID flag incomplete queries
+    uint64_t* out_keys;        // [nq * stride]
+    uint32_t* out_counts;      // [nq]
     uint32_t stride;
+    uint32_t fin_sort_max;     // keys the CTA sort may hold (<= FIN_SORT_MAX, power of two)
+    uint32_t large_in_scratch;
 };
 
-__global__ void __launch_bounds__(FIN_WARPS * 32) finalize_strided_kernel(FinalizeParams p) {
-    __shared__ uint64_t s[SORT_SMALL_MAX];
+__global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(FinalizeParams p) {
+    extern __shared__ __align__(16) uint64_t fin_s[];
     __shared__ uint32_t big_n[FIN_WARPS];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t q = blockIdx.x * FIN_WARPS + warp;
-    uint32_t n = 0, r = 0;
+    const bool in_place = p.out_keys == p.cand;
     if (lane == 0) big_n[warp] = 0;
     if (q < p.nq) {
         const uint32_t c = p.cand_count[q];
-        n = c < p.cap ? c : p.cap;
-        r = (p.limit != 0 && n > p.limit) ? static_cast<uint32_t>(p.limit) : n;
-        if (r > p.stride) r = p.stride;
-        const bool invalid = p.bad[q] == 1;
-        if (lane == 0) p.out_counts[q] = invalid ? COUNT_INVALID : (c > p.cap ? COUNT_OVERFLOW : r);
-        if (c > p.cap || invalid) n = 0;   // flagged: the list would be incomplete / meaningless
+        uint32_t n = c < p.cap ? c : p.cap;
+        const uint32_t r = (p.limit != 0 && n > p.limit) ? static_cast<uint32_t>(p.limit) : n;
+        const bool invalid = p.bad && p.bad[p.qlist ? p.qlist[q] : q] == 1;
+        // more candidates than slots, or a list longer than the caller's stride: flagged like
+        // an overflow -- a cut list must never look like a complete one
+        const bool over = c > p.cap || r > p.stride;
+        if (lane == 0) p.out_counts[q] = invalid ? COUNT_INVALID : (over ? COUNT_OVERFLOW : r);
+        if (over || invalid) n = 0;
         if (n > 32) {
             if (lane == 0) big_n[warp] = n;
         } else if (n > 0) {
@@ -357,17 +290,47 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_strided_kernel(Finali
         const uint32_t bn = big_n[w];
         if (bn == 0) continue;   // uniform across the CTA
         const uint32_t bq = blockIdx.x * FIN_WARPS + w;
+        uint32_t br = (p.limit != 0 && bn > p.limit) ? static_cast<uint32_t>(p.limit) : bn;
+        uint64_t* o = p.out_keys + static_cast<uint64_t>(bq) * p.stride;
+        if (bn > p.fin_sort_max) {
+            // already sorted by sort_large_kernel
+            const uint64_t* keys = (p.large_in_scratch ? p.scratch : p.cand) + static_cast<uint64_t>(bq) * p.cap;
+            if (keys != o)
+                for (uint32_t i = threadIdx.x; i < br; i += blockDim.x) o[i] = keys[i];
+            continue;
+        }
         const uint64_t* keys = p.cand + static_cast<uint64_t>(bq) * p.cap;
         const uint32_t np2 = next_pow2(bn);
-        for (uint32_t i = threadIdx.x; i < np2; i += blockDim.x) s[i] = i < bn ? keys[i] : KEY_PAD;
+        for (uint32_t i = threadIdx.x; i < np2; i += blockDim.x) fin_s[i] = i < bn ? keys[i] : KEY_PAD;
         __syncthreads();
-        block_bitonic_sort(s, np2);
-        uint32_t br = (p.limit != 0 && bn > p.limit) ? static_cast<uint32_t>(p.limit) : bn;
-        if (br > p.stride) br = p.stride;
-        for (uint32_t i = threadIdx.x; i < br; i += blockDim.x)
-            p.out_keys[static_cast<uint64_t>(bq) * p.stride + i] = s[i];
+        block_bitonic_sort(fin_s, np2);
+        for (uint32_t i = threadIdx.x; i < br; i += blockDim.x) o[i] = fin_s[i];
         __syncthreads();
     }
+    (void)in_place;
+}
+
+// CSR formatting of finalized lists: keys of slot qi (sorted in place at cand[qi * cap], count
+// res_count[qi]) -> out_keys[offsets[qi] ...]; CTA 0 also copies the batch's invalid-base flag
+// next to the offsets so that ONE device-to-host copy returns everything.
+struct GatherKeysParams {
+    const uint64_t* cand;
+    const uint32_t* res_count;
+    const uint64_t* offsets;
+    uint32_t cap;
+    uint64_t* out_keys;
+    const int* flags_src;   // d_meta flags
+    int* flags_dst;         // d_out header
+};
+
+__global__ void __launch_bounds__(256) gather_keys_kernel(GatherKeysParams p) {
+    const uint32_t qi = blockIdx.x;
+    if (qi == 0 && threadIdx.x < 2 && p.flags_dst) p.flags_dst[threadIdx.x] = p.flags_src[threadIdx.x];
+    uint32_t r = p.res_count[qi];
+    if (r >= COUNT_INVALID) r = 0;
+    const uint64_t* src = p.cand + static_cast<uint64_t>(qi) * p.cap;
+    uint64_t* dst = p.out_keys + p.offsets[qi];
+    for (uint32_t i = threadIdx.x; i < r; i += blockDim.x) dst[i] = src[i];
 }
 
 // shard merge: per query concatenate n_lists sorted lists, sort, keep the first `limit`.

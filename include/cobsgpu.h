@@ -209,6 +209,24 @@ int cobsgpu_search_batch(cobsgpu_index* idx, const char* queries,
                          uint64_t num_results, cobsgpu_result* out);
 
 /*
+ * Asynchronous pair for callers that stream batches from host buffers: cobsgpu_submit enqueues
+ * one batch (upload + K1 on an input stream, K2 + K3 on the main stream, result download on an
+ * output stream) and returns at once; cobsgpu_collect waits for it and hands out its lists.  Up
+ * to 4 tickets may be outstanding per handle, so the upload of batch i+1 and the download of
+ * batch i-1 overlap the score kernel of batch i (cobsgpu_search_batch pipelines its own
+ * sub-batches the same way).  `queries` must stay valid until the ticket is collected when it
+ * is page-locked memory (pageable memory is staged by the driver before submit returns).
+ * Tickets are collected in any order; the result arrays are valid until the handle has
+ * accepted 4 more batches.  Calls on one handle must come from one thread.
+ * replaces: the per-query loop around Search::search in process_query (src/cobs.cpp:425-462).
+ */
+typedef uint64_t cobsgpu_ticket;
+int cobsgpu_submit(cobsgpu_index* idx, const char* queries, const uint64_t* offsets,
+                   uint32_t nq, double threshold, uint64_t num_results,
+                   cobsgpu_ticket* ticket);
+int cobsgpu_collect(cobsgpu_index* idx, cobsgpu_ticket ticket, cobsgpu_result* out);
+
+/*
  * Device-resident variant used by the multi-GPU path and by bench.py's "value" leg:
  * d_queries is a DEVICE pointer (offsets stay on the host, they drive the launch
  * geometry).  Results stay on the device in caller-provided buffers:
@@ -219,7 +237,10 @@ int cobsgpu_search_batch(cobsgpu_index* idx, const char* queries,
  * instead of an incomplete list (nothing is silently dropped; redo it through
  * cobsgpu_search_batch); a query with a non-ACGT base in a canonicalising index gets
  * COBSGPU_COUNT_INVALID (the host entry points report COBSGPU_ERR_INVALID_BASE for it).
- * Queries are limited to 255 k-mers on this path.
+ * A query whose result list is longer than results_per_query is flagged COBSGPU_COUNT_OVERFLOW
+ * as well (a cut list never looks like a complete one).  With 1 <= num_results <= 1024 the
+ * per-warp top-k epilogue bounds every list, so nothing overflows when results_per_query >=
+ * num_results.  Queries are limited to 65 535 k-mers on this path.
  * All work is enqueued on `stream` (a cudaStream_t, may be 0) and is asynchronous; calls on
  * one handle must be issued from one thread, and the stream must be synchronised before the
  * host-buffer entry points are used on the same handle.
