@@ -5,4 +5,4 @@ include/cobsgpu.h); this package is the ctypes binding plus a mirror of the refe
 Python `Search` class.  No CPU fallback exists.
 """
 from ._lib import CobsGpuError, KIND_CLASSIC, KIND_COMPACT, LIB_PATH, lib  # noqa: F401
-from .api import GpuIndex, Search, SearchResult, decode_keys, merge_device  # noqa: F401
+from .api import GpuGroup, GpuIndex, Search, SearchResult, decode_keys, merge_device  # noqa: F401

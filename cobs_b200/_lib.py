@@ -134,6 +134,15 @@ SYMBOLS = {
     "cobsgpu_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_double,
                                  C.c_uint64, C.POINTER(C.c_uint64)]),
     "cobsgpu_collect": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(Result)]),
+    "cobsgpu_group_open_file": (C.c_int, [C.c_char_p, C.POINTER(C.c_int32), C.c_uint32,
+                                          C.POINTER(C.c_void_p)]),
+    "cobsgpu_group_open": (C.c_int, [C.POINTER(IndexDesc), C.POINTER(C.c_int32), C.c_uint32,
+                                     C.POINTER(C.c_void_p)]),
+    "cobsgpu_group_close": (None, [C.c_void_p]),
+    "cobsgpu_group_size": (C.c_uint32, [C.c_void_p]),
+    "cobsgpu_group_shard": (C.c_void_p, [C.c_void_p, C.c_uint32]),
+    "cobsgpu_group_search_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                             C.c_double, C.c_uint64, C.POINTER(Result)]),
     "cobsgpu_search_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                               C.c_double, C.c_uint64, C.c_uint32, C.c_void_p,
                                               C.c_void_p, C.c_void_p]),

@@ -262,6 +262,80 @@ class GpuIndex:
         return out
 
 
+class GpuGroup:
+    """One index sharded along the document axis over several GPUs of THIS process (shard g on
+    devices[g]); the leader GPU merges the shards' result blocks over NVLink.  Same search
+    interface as GpuIndex."""
+
+    def __init__(self, handle):
+        self._g = C.c_void_p(handle)
+        n = _lib.lib().cobsgpu_group_size(self._g)
+        self.shards = []
+        for i in range(n):
+            ix = GpuIndex(_lib.lib().cobsgpu_group_shard(self._g, i))
+            ix.close = lambda: None          # borrowed: the group owns its shards
+            self.shards.append(ix)
+        self.info = self.shards[0].info
+
+    @classmethod
+    def open_file(cls, path, devices):
+        g = C.c_void_p()
+        p = path if isinstance(path, bytes) else str(path).encode()
+        dev = (C.c_int32 * len(devices))(*devices)
+        _lib.check(_lib.lib().cobsgpu_group_open_file(p, dev, len(devices), C.byref(g)))
+        return cls(g.value)
+
+    @classmethod
+    def procedural(cls, kind, n_docs, signature_sizes, num_hashes, devices, page_size=0,
+                   term_size=31, canonicalize=1, fill_seed=1):
+        sig = np.ascontiguousarray(signature_sizes, dtype=np.uint64)
+        d = _lib.IndexDesc()
+        d.struct_size = C.sizeof(_lib.IndexDesc)
+        d.kind = kind
+        d.term_size = term_size
+        d.canonicalize = canonicalize
+        d.num_hashes = num_hashes
+        d.n_docs = n_docs
+        d.n_pages = len(sig)
+        d.page_size = page_size if kind == KIND_COMPACT else (n_docs + 7) // 8
+        d.signature_sizes = sig.ctypes.data_as(C.POINTER(C.c_uint64))
+        d.page_data = None
+        d.fill_seed = fill_seed
+        g = C.c_void_p()
+        dev = (C.c_int32 * len(devices))(*devices)
+        _lib.check(_lib.lib().cobsgpu_group_open(C.byref(d), dev, len(devices), C.byref(g)))
+        return cls(g.value)
+
+    def set_option(self, name, value):
+        for s in self.shards:
+            s.set_option(name, value)
+
+    def search_batch(self, queries, threshold=0.0, num_results=0):
+        blob, off = _pack_queries(queries)
+        return self.search_packed(blob, off, threshold, num_results)
+
+    def search_packed(self, blob, off, threshold=0.0, num_results=0, raw=False):
+        nq = len(off) - 1
+        r = _lib.Result()
+        bp = blob.ctypes.data if isinstance(blob, np.ndarray) else blob
+        _lib.check(_lib.lib().cobsgpu_group_search_batch(self._g, bp, off.ctypes.data, nq,
+                                                         threshold, num_results, C.byref(r)))
+        return GpuIndex._unpack(r, nq, raw)
+
+    def close(self):
+        if self._g:
+            for s in self.shards:
+                s._h = None
+            _lib.lib().cobsgpu_group_close(self._g)
+            self._g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def merge_device(device, n_lists, nq, results_per_query, d_counts_ptr, d_keys_ptr, num_results,
                  out_per_query, d_out_counts_ptr, d_out_keys_ptr, stream=0,
                  counts_list_stride=0, keys_list_stride=0):

@@ -22,6 +22,7 @@
 #include <functional>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -76,10 +77,13 @@ struct DevBuf {
     size_t cap = 0;
     void ensure(size_t n) {
         if (n <= cap) return;
+        reserve(round_up<size_t>(n + n / 4, 256));
+    }
+    void reserve(size_t n) {   // exact capacity, contents are not kept
+        if (n <= cap) return;
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
-        n = round_up<size_t>(n + n / 4, 256);
         CK(cudaMalloc(&p, n));
         cap = n;
     }
@@ -97,10 +101,13 @@ struct PinBuf {
     size_t cap = 0;
     void ensure(size_t n) {
         if (n <= cap) return;
+        reserve(round_up<size_t>(n + n / 4, 256));
+    }
+    void reserve(size_t n) {   // exact capacity, contents are not kept
+        if (n <= cap) return;
         if (p) cudaFreeHost(p);
         p = nullptr;
         cap = 0;
-        n = round_up<size_t>(n + n / 4, 256);
         CK(cudaMallocHost(&p, n));
         cap = n;
     }
@@ -194,6 +201,30 @@ struct Slot {
     cudaEvent_t& ev(cudaEvent_t& e) {
         if (!e) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
         return e;
+    }
+    // total capacity of the buffers: changes exactly when one of them grew
+    size_t footprint() const {
+        size_t n = h_meta.cap + h_out.cap;
+        for (const DevBuf* b : { &d_queries, &d_meta, &d_hashes, &d_cand, &d_scratch, &d_res_count,
+                                 &d_out, &d_qlist, &d_dense })
+            n += b->cap;
+        return n;
+    }
+    // grows this (idle) slot's buffers to the capacities of `o`: allocations synchronise the
+    // device, so the whole ring is sized during the first batch instead of once per slot
+    void match(const Slot& o) {
+        DevBuf* mine[] = { &d_queries, &d_meta, &d_hashes, &d_cand, &d_scratch, &d_res_count,
+                           &d_out, &d_qlist, &d_dense };
+        const DevBuf* theirs[] = { &o.d_queries, &o.d_meta, &o.d_hashes, &o.d_cand, &o.d_scratch,
+                                   &o.d_res_count, &o.d_out, &o.d_qlist, &o.d_dense };
+        for (size_t i = 0; i < sizeof(mine) / sizeof(mine[0]); ++i) {
+            if (mine[i]->cap < theirs[i]->cap) {
+                if (mine[i] == &d_meta) meta_resident = false;
+                mine[i]->reserve(theirs[i]->cap);
+            }
+        }
+        h_meta.reserve(o.h_meta.cap);
+        h_out.reserve(o.h_out.cap);
     }
     void release() {
         for (cudaEvent_t* e : { &ev_meta, &ev_in, &ev_main, &ev_out })
@@ -849,7 +880,9 @@ void launch_select(cobsgpu_index* ix, const Slot& src, Slot& work, const uint32_
     const uint32_t cap = pl.cap;
     uint64_t* cand = work.d_cand.as<uint64_t>();
     bool large_in_scratch = false;
-    if (cap > FIN_SORT_MAX) {
+    // (limits of at most 32 are served by finalize_kernel's streaming selection, whatever the
+    // length of the candidate list)
+    if (cap > FIN_SORT_MAX && !(pl.limit >= 1 && pl.limit <= 32)) {
         work.d_scratch.ensure(static_cast<uint64_t>(n_slots) * cap * 8);
         SortLargeParams lp{};
         lp.cand = cand;
@@ -1073,6 +1106,24 @@ bool plan_main_pass(const cobsgpu_index* ix, const Slot& sl, double threshold, u
     return false;
 }
 
+// On scope exit: when this slot had to grow a buffer, the idle slots of the ring follow at once.
+// Allocations synchronise the device, so the whole ring is sized during the first batch instead
+// of stalling once per slot.
+struct WarmRing {
+    cobsgpu_index* ix;
+    Slot& sl;
+    size_t before;
+    ~WarmRing() {
+        if (sl.footprint() == before) return;
+        try {
+            for (Slot& o : ix->slots)
+                if (&o != &sl && !o.busy) o.match(sl);
+        } catch (const Err&) {   // best effort: the slot allocates on its own turn instead
+            cudaGetLastError();
+        }
+    }
+};
+
 Slot& take_slot(cobsgpu_index* ix) {
     Slot& sl = ix->slots[ix->next_slot];
     if (sl.busy)
@@ -1088,6 +1139,7 @@ Slot& take_slot(cobsgpu_index* ix) {
 Slot& submit_batch(cobsgpu_index* ix, const char* queries, const uint64_t* offsets, uint32_t q0,
                    uint32_t q1, double threshold, uint64_t limit) {
     Slot& sl = take_slot(ix);
+    WarmRing warm{ ix, sl, sl.footprint() };
     prepare_batch(ix, sl, queries, false, offsets, q0, q1, threshold, ix->s_in);
     CK(cudaEventRecord(sl.ev(sl.ev_in), ix->s_in));
     const uint32_t nq = q1 - q0;
@@ -1260,6 +1312,346 @@ void drop_tickets(cobsgpu_index* ix) {
     for (cudaStream_t st : { ix->s_in, ix->stream, ix->s_out })
         if (st) cudaStreamSynchronize(st);
     for (Slot& sl : ix->slots) sl.busy = false;
+}
+
+// ---------------------------------------------------------------------------------------
+// CSR formatting with explicit list pointers (the group's merged lists live beside the
+// leader's own candidates)
+void launch_csr_lists(cobsgpu_index* ix, const Slot& src, Slot& work, uint32_t n_slots,
+                      const uint64_t* lists, const uint32_t* counts, uint32_t stride,
+                      cudaStream_t st) {
+    PhaseScope ps(ix, PH_SELECT, st);
+    scan_offsets_kernel<<<1, 1024, 0, st>>>(counts, n_slots, work.o_off());
+    CK(cudaGetLastError());
+    GatherKeysParams gp{ lists, counts, work.o_off(), stride, work.o_keys(), src.d_flags(),
+                         work.o_flags() };
+    gather_keys_kernel<<<n_slots, 256, 0, st>>>(gp);
+    CK(cudaGetLastError());
+    ix->tm.kernel_launches += 2;
+}
+
+}  // namespace
+
+// A document-sharded index spread over several GPUs of ONE process: shard g lives on
+// devices[g]; shard 0's device is the leader that merges.  Every shard runs K1-K3 on its own
+// streams; the leader's merge kernel then reads the peers' fixed-size result blocks
+// [nq][rpq] straight out of their HBM over NVLink (peer access) -- the one exchange of the
+// path, k * 8 bytes per query per shard -- and returns ONE ordered list
+// per query to the host.
+struct cobsgpu_group {
+    std::vector<cobsgpu_index*> shards;
+    std::vector<int> devices;
+    std::vector<char> peer_ok;       // leader can map shard g's memory
+    struct GSlot {
+        bool busy = false;
+        int mode = 0;                // 0: merged on the leader, -1: per-shard host path
+        uint32_t q0 = 0, nq = 0;
+        uint32_t rpq = 0, out_stride = 0;
+        double threshold = 0;
+        uint64_t limit = 0;
+        uint64_t spec_keys = 0;
+        std::vector<Slot*> sl;       // the shards' slots of this batch
+        DevBuf d_mkeys, d_mcount;    // merged lists on the leader
+        DevBuf d_stage_keys, d_stage_counts;   // copies of peers' blocks when peer access is missing
+        std::vector<uint64_t> r_off;
+        std::vector<uint32_t> r_doc, r_score;
+    } gs[cobsgpu_index::N_SLOTS];
+    int next = 0;
+    // result of the last cobsgpu_group_search_batch call
+    std::vector<uint64_t> r_off;
+    std::vector<uint32_t> r_doc, r_score;
+    // a copy of the caller's queries that stays valid while batches are in flight is not
+    // needed: cudaMemcpyAsync from pageable memory is staged before it returns
+
+    ~cobsgpu_group() {
+        for (auto& g : gs) {
+            if (!devices.empty()) cudaSetDevice(devices[0]);
+            g = GSlot();
+        }
+        for (cobsgpu_index* ix : shards) delete ix;
+    }
+};
+
+namespace {
+
+using GSlot = cobsgpu_group::GSlot;
+
+void group_finish_open(cobsgpu_group* grp) {
+    const size_t n = grp->shards.size();
+    grp->peer_ok.assign(n, 1);
+    CK(cudaSetDevice(grp->devices[0]));
+    for (size_t g = 1; g < n; ++g) {
+        if (grp->devices[g] == grp->devices[0]) continue;   // (tests: several shards on one GPU)
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, grp->devices[0], grp->devices[g]);
+        if (can) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(grp->devices[g], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) can = 0;
+            cudaGetLastError();
+        }
+        grp->peer_ok[g] = static_cast<char>(can);
+    }
+}
+
+void group_drop(cobsgpu_group* grp) {
+    for (cobsgpu_index* ix : grp->shards) {
+        cudaSetDevice(ix->device);
+        drop_tickets(ix);
+    }
+    for (auto& g : grp->gs) g.busy = false;
+}
+
+// Enqueues queries [q0, q1) on every shard and the merge on the leader.  Nothing waits.
+GSlot& group_submit(cobsgpu_group* grp, const char* queries, const uint64_t* offsets, uint32_t q0,
+                    uint32_t q1, double threshold, uint64_t limit) {
+    GSlot& gsl = grp->gs[grp->next];
+    if (gsl.busy) throw Err{ COBSGPU_ERR_INVALID_ARG, "too many group batches in flight" };
+    grp->next = (grp->next + 1) % cobsgpu_index::N_SLOTS;
+    const uint32_t n = static_cast<uint32_t>(grp->shards.size());
+    const uint32_t nq = q1 - q0;
+    gsl.q0 = q0;
+    gsl.nq = nq;
+    gsl.threshold = threshold;
+    gsl.limit = limit;
+    gsl.sl.assign(n, nullptr);
+    gsl.mode = 0;
+    // one stride for every shard: a small limit bounds each list (top-k epilogue), otherwise
+    // the candidate slots, cut so that the merge fits its shared memory
+    const bool topk = limit >= 1 && limit <= TOPK_MAX_K && limit * n <= MERGE_MAX;
+    if (!topk && !(threshold > 0.0)) gsl.mode = -1;   // every document passes: per-shard exhaustive
+    // (queries beyond 16 bit-planes are rare: such a batch takes the per-shard host path too)
+    const uint64_t k = grp->shards[0]->term_size;
+    for (uint32_t q = q0; q < q1 && gsl.mode == 0; ++q)
+        if (offsets[q + 1] >= offsets[q] && offsets[q + 1] - offsets[q] > MAX_T_LONG + k - 1) gsl.mode = -1;
+    uint32_t rpq = 1;
+    if (gsl.mode == 0) {
+        uint32_t mc = 1;
+        for (cobsgpu_index* ix : grp->shards) mc = std::max(mc, ix->max_candidates);
+        rpq = topk ? static_cast<uint32_t>(limit) : std::min<uint32_t>(mc, MERGE_MAX / n);
+    }
+    gsl.rpq = rpq;
+    for (uint32_t g = 0; g < n; ++g) {
+        cobsgpu_index* ix = grp->shards[g];
+        CK(cudaSetDevice(ix->device));
+        if (gsl.mode < 0) {
+            gsl.sl[g] = &submit_batch(ix, queries, offsets, q0, q1, threshold, limit);
+            continue;
+        }
+        Slot& sl = take_slot(ix);
+        WarmRing warm{ ix, sl, sl.footprint() };
+        sl.busy = true;
+        sl.ticket = ++ix->ticket_counter;
+        gsl.sl[g] = &sl;
+        prepare_batch(ix, sl, queries, false, offsets, q0, q1, threshold, ix->s_in);
+        CK(cudaEventRecord(sl.ev(sl.ev_in), ix->s_in));
+        cudaStream_t st = ix->stream;
+        CK(cudaStreamWaitEvent(st, sl.ev_in, 0));
+        PassPlan pl;
+        pl.lng = sl.max_T > MAX_T_SHORT;
+        pl.limit = limit;
+        const uint32_t real = std::max<uint32_t>(ix->shard_real_docs, 1);
+        if (topk) {
+            pl.mode = MODE_TOPK;
+            pl.cap = static_cast<uint32_t>(std::max<uint64_t>(
+                1, std::min<uint64_t>(static_cast<uint64_t>(ix->warps_per_query) * limit, real)));
+        } else {
+            pl.mode = MODE_CAND;
+            pl.cap = std::min<uint32_t>(std::max<uint32_t>(rpq, ix->max_candidates), real);
+        }
+        sl.layout_out(nq);
+        sl.d_out.ensure(sl.out_keys);
+        sl.d_res_count.ensure(static_cast<size_t>(nq) * 4);
+        sl.d_scratch.ensure(1);
+        // the shard's result block [nq][rpq] lives in d_dense (unused on this path)
+        sl.d_dense.ensure(static_cast<uint64_t>(nq) * rpq * 8);
+        launch_pass_score(ix, sl, sl, nullptr, nq, pl, sl.o_cc(), st);
+        launch_select(ix, sl, sl, nullptr, nq, pl, sl.max_T, sl.o_cc(), sl.d_dense.as<uint64_t>(),
+                      sl.d_res_count.as<uint32_t>(), rpq, true, st);
+        CK(cudaEventRecord(sl.ev(sl.ev_main), st));
+    }
+    gsl.busy = true;
+    if (gsl.mode < 0) return gsl;
+
+    // ---- the exchange + merge on the leader ----
+    cobsgpu_index* lead = grp->shards[0];
+    Slot& ls = *gsl.sl[0];
+    CK(cudaSetDevice(lead->device));
+    cudaStream_t st = lead->stream;
+    MergeParams mp{};
+    for (uint32_t g = 0; g < n; ++g) {
+        Slot& sl = *gsl.sl[g];
+        if (g) CK(cudaStreamWaitEvent(st, sl.ev_main, 0));
+        const uint32_t* counts = sl.d_res_count.as<uint32_t>();
+        const uint64_t* keys = sl.d_dense.as<uint64_t>();
+        if (g && !grp->peer_ok[g]) {
+            // no peer mapping: copy the block into a staging area on the leader instead
+            gsl.d_stage_counts.ensure(static_cast<size_t>(n) * nq * 4);
+            gsl.d_stage_keys.ensure(static_cast<size_t>(n) * nq * rpq * 8);
+            uint32_t* dc = gsl.d_stage_counts.as<uint32_t>() + static_cast<size_t>(g) * nq;
+            uint64_t* dk = gsl.d_stage_keys.as<uint64_t>() + static_cast<size_t>(g) * nq * rpq;
+            CK(cudaMemcpyPeerAsync(dc, lead->device, counts, grp->shards[g]->device,
+                                   static_cast<size_t>(nq) * 4, st));
+            CK(cudaMemcpyPeerAsync(dk, lead->device, keys, grp->shards[g]->device,
+                                   static_cast<size_t>(nq) * rpq * 8, st));
+            counts = dc;
+            keys = dk;
+        }
+        mp.counts[g] = counts;
+        mp.keys[g] = keys;
+    }
+    const uint64_t all = static_cast<uint64_t>(n) * rpq;
+    gsl.out_stride = static_cast<uint32_t>(limit ? std::min<uint64_t>(limit, all) : all);
+    gsl.d_mkeys.ensure(static_cast<uint64_t>(nq) * gsl.out_stride * 8);
+    gsl.d_mcount.ensure(static_cast<size_t>(nq) * 4);
+    mp.n_lists = n;
+    mp.nq = nq;
+    mp.stride = rpq;
+    mp.limit = limit;
+    mp.out_stride = gsl.out_stride;
+    mp.out_counts = gsl.d_mcount.as<uint32_t>();
+    mp.out_keys = gsl.d_mkeys.as<uint64_t>();
+    {
+        PhaseScope ps(lead, PH_SELECT, st);
+        const size_t smem = static_cast<size_t>(pow2_ceil(static_cast<uint32_t>(all))) * 8;
+        CK(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(MERGE_MAX * 8)));
+        merge_kernel<<<nq, 256, smem, st>>>(mp);
+        CK(cudaGetLastError());
+        lead->tm.kernel_launches++;
+    }
+    // CSR + one copy back, like the single-GPU path; the header's cand_count words carry the
+    // merged counts so that flagged queries are visible to the host
+    ls.layout_out(nq);
+    const size_t ob = ls.out_keys + static_cast<size_t>(nq) * gsl.out_stride * 8;
+    ls.d_out.ensure(ob);
+    launch_csr_lists(lead, ls, ls, nq, gsl.d_mkeys.as<uint64_t>(), gsl.d_mcount.as<uint32_t>(),
+                     gsl.out_stride, st);
+    CK(cudaMemcpyAsync(ls.o_cc(), gsl.d_mcount.p, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToDevice, st));
+    CK(cudaEventRecord(ls.ev(ls.ev_main), st));
+    gsl.spec_keys = std::min<uint64_t>(static_cast<uint64_t>(nq) * gsl.out_stride,
+                                       std::max<uint64_t>(8192, 8ull * nq));
+    ls.h_out.ensure(ls.out_keys + gsl.spec_keys * 8);
+    CK(cudaStreamWaitEvent(lead->s_out, ls.ev_main, 0));
+    {
+        PhaseScope ps(lead, PH_D2H, lead->s_out);
+        CK(cudaMemcpyAsync(ls.h_out.p, ls.d_out.p, ls.out_keys + gsl.spec_keys * 8, cudaMemcpyDeviceToHost,
+                           lead->s_out));
+    }
+    CK(cudaEventRecord(ls.ev(ls.ev_out), lead->s_out));
+    return gsl;
+}
+
+// merges per-shard host lists of one query (each ordered) into `out` under the global order
+void host_merge(std::vector<uint64_t>& keys, uint64_t limit) {
+    std::sort(keys.begin(), keys.end());
+    if (limit && keys.size() > limit) keys.resize(limit);
+}
+
+void group_collect(cobsgpu_group* grp, GSlot& gsl) {
+    if (!gsl.busy) throw Err{ COBSGPU_ERR_INVALID_ARG, "group batch is not in flight" };
+    const uint32_t n = static_cast<uint32_t>(grp->shards.size());
+    const uint32_t nq = gsl.nq;
+    struct Release {
+        cobsgpu_group* grp;
+        GSlot& g;
+        ~Release() {
+            g.busy = false;
+            for (Slot* s : g.sl)
+                if (s) s->busy = false;
+        }
+    } release{ grp, gsl };
+    gsl.r_off.assign(1, 0);
+    gsl.r_doc.clear();
+    gsl.r_score.clear();
+    // queries that need the per-shard host path: all of them (mode -1) or the flagged ones
+    std::vector<uint32_t> redo;
+    std::vector<uint64_t> off_main;
+    const uint64_t* keys_main = nullptr;
+    if (gsl.mode < 0) {
+        redo.resize(nq);
+        for (uint32_t i = 0; i < nq; ++i) redo[i] = i;
+    } else {
+        cobsgpu_index* lead = grp->shards[0];
+        Slot& ls = *gsl.sl[0];
+        CK(cudaSetDevice(lead->device));
+        CK(cudaEventSynchronize(ls.ev_out));
+        // the peers' streams have finished too: the merge waited for them
+        const char* h = ls.h_out.as<char>();
+        const int* flags = ls.h_out.as<int>();
+        if (flags[0] != FLAG_CLEAR) throw_bad_base(gsl.q0 + static_cast<uint32_t>(flags[0]));
+        const uint64_t* off = reinterpret_cast<const uint64_t*>(h + ls.out_off);
+        const uint64_t total = off[nq];
+        if (total > gsl.spec_keys) {
+            ls.h_out.ensure_keep(ls.out_keys + total * 8, ls.out_keys + gsl.spec_keys * 8);
+            h = ls.h_out.as<char>();
+            off = reinterpret_cast<const uint64_t*>(h + ls.out_off);
+            CK(cudaMemcpyAsync(ls.h_out.as<char>() + ls.out_keys + gsl.spec_keys * 8,
+                               ls.o_keys() + gsl.spec_keys, (total - gsl.spec_keys) * 8,
+                               cudaMemcpyDeviceToHost, lead->s_out));
+            CK(cudaStreamSynchronize(lead->s_out));
+        }
+        const uint32_t* cc = reinterpret_cast<const uint32_t*>(h + ls.out_cc);
+        for (uint32_t i = 0; i < nq; ++i)
+            if (cc[i] == COUNT_OVERFLOW) redo.push_back(i);
+        off_main.assign(off, off + nq + 1);
+        keys_main = reinterpret_cast<const uint64_t*>(h + ls.out_keys);
+        if (redo.empty()) {
+            gsl.r_off.swap(off_main);
+            gsl.r_doc.resize(total);
+            gsl.r_score.resize(total);
+            decode_keys(keys_main, total, gsl.r_doc.data(), gsl.r_score.data());
+            return;
+        }
+    }
+    // per-shard host path for the remaining queries + merge on the host
+    std::vector<std::vector<uint64_t>> merged(redo.size());
+    if (gsl.mode < 0) {
+        for (uint32_t g = 0; g < n; ++g) {
+            cobsgpu_index* ix = grp->shards[g];
+            CK(cudaSetDevice(ix->device));
+            Slot& sl = *gsl.sl[g];
+            collect_batch(ix, sl);
+            for (uint32_t i = 0; i < nq; ++i)
+                for (uint64_t e = sl.r_off[i]; e < sl.r_off[i + 1]; ++e)
+                    merged[i].push_back(make_key(sl.r_score[e], sl.r_doc[e]));
+        }
+    } else {
+        // flagged queries: re-run them through every shard's own host path (which falls back
+        // to its exhaustive pass), straight from the hashes still resident in the shard's slot
+        for (uint32_t g = 0; g < n; ++g) {
+            cobsgpu_index* ix = grp->shards[g];
+            CK(cudaSetDevice(ix->device));
+            std::vector<HostList> lists;
+            std::vector<std::pair<uint32_t, uint32_t>> where(nq, { 0u, 0u });
+            run_exhaustive(ix, *gsl.sl[g], redo, gsl.limit, &lists, &where);
+            for (size_t j = 0; j < redo.size(); ++j) {
+                const HostList& L = lists[where[redo[j]].first];
+                const uint32_t s = where[redo[j]].second;
+                for (uint64_t e = L.off[s]; e < L.off[s + 1]; ++e)
+                    merged[j].push_back(make_key(L.score[e], L.doc[e]));
+            }
+        }
+    }
+    for (auto& m : merged) host_merge(m, gsl.limit);
+    size_t rj = 0;
+    uint64_t run = 0;
+    for (uint32_t i = 0; i < nq; ++i) {
+        if (rj < redo.size() && redo[rj] == i) {
+            for (uint64_t key : merged[rj]) {
+                gsl.r_doc.push_back(key_doc(key));
+                gsl.r_score.push_back(key_score(key));
+            }
+            run += merged[rj].size();
+            ++rj;
+        } else {
+            for (uint64_t e = off_main[i]; e < off_main[i + 1]; ++e) {
+                gsl.r_doc.push_back(key_doc(keys_main[e]));
+                gsl.r_score.push_back(key_score(keys_main[e]));
+            }
+            run += off_main[i + 1] - off_main[i];
+        }
+        gsl.r_off.push_back(run);
+    }
 }
 
 }  // namespace
@@ -1732,6 +2124,110 @@ int cobsgpu_collect(cobsgpu_index* ix, cobsgpu_ticket ticket, cobsgpu_result* ou
     });
 }
 
+int cobsgpu_group_open_file(const char* path, const int32_t* devices, uint32_t n_devices,
+                            cobsgpu_group** out) {
+    return guarded([&] {
+        if (!path || !devices || !out || n_devices == 0 || n_devices > MERGE_MAX_LISTS)
+            throw Err{ COBSGPU_ERR_INVALID_ARG, "a group holds 1..16 shards" };
+        std::unique_ptr<cobsgpu_group> grp(new cobsgpu_group);
+        // the shards load concurrently: one host thread per GPU, each streaming its own columns
+        std::vector<cobsgpu_index*> ix(n_devices, nullptr);
+        std::vector<int> rc(n_devices, COBSGPU_OK);
+        std::vector<std::string> err(n_devices);
+        std::vector<std::thread> th;
+        for (uint32_t g = 0; g < n_devices; ++g)
+            th.emplace_back([&, g] {
+                rc[g] = cobsgpu_index_open_file(path, devices[g], g, n_devices, &ix[g]);
+                if (rc[g] != COBSGPU_OK) err[g] = g_error;   // thread-local: read it here
+            });
+        for (auto& t : th) t.join();
+        for (uint32_t g = 0; g < n_devices; ++g)
+            if (ix[g]) {   // (the group's destructor closes whatever did open)
+                grp->shards.push_back(ix[g]);
+                grp->devices.push_back(devices[g]);
+            }
+        for (uint32_t g = 0; g < n_devices; ++g)
+            if (rc[g] != COBSGPU_OK) throw Err{ rc[g], err[g] };
+        group_finish_open(grp.get());
+        *out = grp.release();
+    });
+}
+
+int cobsgpu_group_open(const cobsgpu_index_desc* desc, const int32_t* devices, uint32_t n_devices,
+                       cobsgpu_group** out) {
+    return guarded([&] {
+        if (!desc || !devices || !out || n_devices == 0 || n_devices > MERGE_MAX_LISTS)
+            throw Err{ COBSGPU_ERR_INVALID_ARG, "a group holds 1..16 shards" };
+        std::unique_ptr<cobsgpu_group> grp(new cobsgpu_group);
+        for (uint32_t g = 0; g < n_devices; ++g) {
+            cobsgpu_index_desc d = *desc;
+            d.device = devices[g];
+            d.shard_index = g;
+            d.shard_count = n_devices;
+            cobsgpu_index* ix = nullptr;
+            const int rc = cobsgpu_index_open(&d, &ix);
+            if (rc != COBSGPU_OK) throw Err{ rc, g_error };
+            grp->shards.push_back(ix);
+            grp->devices.push_back(devices[g]);
+        }
+        group_finish_open(grp.get());
+        *out = grp.release();
+    });
+}
+
+void cobsgpu_group_close(cobsgpu_group* grp) { delete grp; }
+
+uint32_t cobsgpu_group_size(const cobsgpu_group* grp) {
+    return grp ? static_cast<uint32_t>(grp->shards.size()) : 0;
+}
+
+cobsgpu_index* cobsgpu_group_shard(cobsgpu_group* grp, uint32_t i) {
+    return (grp && i < grp->shards.size()) ? grp->shards[i] : nullptr;
+}
+
+int cobsgpu_group_search_batch(cobsgpu_group* grp, const char* queries, const uint64_t* offsets,
+                               uint32_t nq, double threshold, uint64_t num_results,
+                               cobsgpu_result* out) {
+    return guarded([&] {
+        if (!grp || !offsets || (!queries && nq) || !out || grp->shards.empty())
+            throw Err{ COBSGPU_ERR_INVALID_ARG, "null argument" };
+        for (cobsgpu_index* ix : grp->shards) check_idle(ix);
+        grp->r_off.assign(1, 0);
+        grp->r_doc.clear();
+        grp->r_score.clear();
+        // batch boundaries: the tightest of the shards' (workspace, max_batch); pipelined
+        // through the ring like cobsgpu_search_batch
+        std::vector<GSlot*> inflight;
+        size_t head = 0;
+        auto drain_one = [&] {
+            GSlot& g = *inflight[head++];
+            group_collect(grp, g);
+            const uint64_t base = grp->r_off.back();
+            for (size_t i = 1; i < g.r_off.size(); ++i) grp->r_off.push_back(base + g.r_off[i]);
+            grp->r_doc.insert(grp->r_doc.end(), g.r_doc.begin(), g.r_doc.end());
+            grp->r_score.insert(grp->r_score.end(), g.r_score.begin(), g.r_score.end());
+        };
+        try {
+            for (uint32_t q0 = 0; q0 < nq;) {
+                uint32_t q1 = nq;
+                for (cobsgpu_index* ix : grp->shards)
+                    q1 = std::min(q1, next_batch_end(ix, offsets, q0, nq, num_results));
+                if (inflight.size() - head == cobsgpu_index::N_SLOTS - 1) drain_one();
+                inflight.push_back(&group_submit(grp, queries, offsets, q0, q1, threshold, num_results));
+                q0 = q1;
+            }
+            while (head < inflight.size()) drain_one();
+        } catch (...) {
+            group_drop(grp);
+            throw;
+        }
+        for (cobsgpu_index* ix : grp->shards) resolve_timers(ix);
+        out->offsets = grp->r_off.data();
+        out->doc = grp->r_doc.data();
+        out->score = grp->r_score.data();
+    });
+}
+
 int cobsgpu_search_batch_device(cobsgpu_index* ix, const char* d_queries, const uint64_t* offsets,
                                 uint32_t nq, double threshold, uint64_t num_results,
                                 uint32_t results_per_query, uint32_t* d_counts, uint64_t* d_keys,
@@ -1743,6 +2239,7 @@ int cobsgpu_search_batch_device(cobsgpu_index* ix, const char* d_queries, const 
         CK(cudaSetDevice(ix->device));
         cudaStream_t st = static_cast<cudaStream_t>(stream);
         Slot& sl = take_slot(ix);
+        WarmRing warm{ ix, sl, sl.footprint() };
         // "prefetch": metadata upload + K1 run ahead on s_in, in a slot no earlier call still
         // reads, and only K2/K3 are ordered on the caller's stream
         cudaStream_t ks = st;
@@ -1804,11 +2301,22 @@ int cobsgpu_merge_device(int device, uint32_t n_lists, uint32_t nq, uint32_t res
         const size_t smem = static_cast<size_t>(np2) * 8;
         CK(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
-        MergeParams mp{ d_counts, d_keys,
-                        counts_list_stride ? counts_list_stride : nq,
-                        keys_list_stride ? keys_list_stride : static_cast<uint64_t>(nq) * results_per_query,
-                        n_lists, nq, results_per_query, num_results,
-                        out_per_query, d_out_counts, d_out_keys };
+        if (n_lists > MERGE_MAX_LISTS)
+            throw Err{ COBSGPU_ERR_INVALID_ARG, "merge handles at most 16 lists" };
+        const uint64_t cs = counts_list_stride ? counts_list_stride : nq;
+        const uint64_t ks = keys_list_stride ? keys_list_stride : static_cast<uint64_t>(nq) * results_per_query;
+        MergeParams mp{};
+        for (uint32_t l = 0; l < n_lists; ++l) {
+            mp.counts[l] = d_counts + l * cs;
+            mp.keys[l] = d_keys + l * ks;
+        }
+        mp.n_lists = n_lists;
+        mp.nq = nq;
+        mp.stride = results_per_query;
+        mp.limit = num_results;
+        mp.out_stride = out_per_query;
+        mp.out_counts = d_out_counts;
+        mp.out_keys = d_out_keys;
         merge_kernel<<<nq, 256, smem, static_cast<cudaStream_t>(stream)>>>(mp);
         CK(cudaGetLastError());
     });

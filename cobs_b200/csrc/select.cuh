@@ -269,7 +269,30 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(FinalizeParams
         const bool over = c > p.cap || r > p.stride;
         if (lane == 0) p.out_counts[q] = invalid ? COUNT_INVALID : (over ? COUNT_OVERFLOW : r);
         if (over || invalid) n = 0;
-        if (n > 32) {
+        if (n > 32 && p.limit != 0 && p.limit <= 32) {
+            // Streaming selection for small limits (`-l 10`): `best` holds the k smallest keys
+            // seen so far, sorted over the lanes; a chunk of 32 candidates is tested against the
+            // current k-th key with one ballot and only the few that beat it are inserted
+            // (expected k * ln(n / k) insertions).  No shared memory, no sort of the whole list.
+            const uint32_t k = static_cast<uint32_t>(p.limit);
+            const uint64_t* keys = p.cand + static_cast<uint64_t>(q) * p.cap;
+            uint64_t best = KEY_PAD;
+            for (uint32_t base = 0; base < n; base += 32) {
+                const uint64_t key = base + lane < n ? keys[base + lane] : KEY_PAD;
+                const uint64_t kth = __shfl_sync(0xFFFFFFFFu, best, k - 1);
+                uint32_t m = __ballot_sync(0xFFFFFFFFu, key < kth);
+                while (m) {
+                    const uint32_t src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint64_t x = __shfl_sync(0xFFFFFFFFu, key, src);
+                    const uint32_t pos = __popc(__ballot_sync(0xFFFFFFFFu, best < x));
+                    const uint64_t up = __shfl_up_sync(0xFFFFFFFFu, best, 1);
+                    if (lane > pos) best = up;
+                    else if (lane == pos) best = x;
+                }
+            }
+            if (lane < r) p.out_keys[static_cast<uint64_t>(q) * p.stride + lane] = best;
+        } else if (n > 32) {
             if (lane == 0) big_n[warp] = n;
         } else if (n > 0) {
             uint64_t key = lane < n ? p.cand[static_cast<uint64_t>(q) * p.cap + lane] : KEY_PAD;
@@ -333,11 +356,14 @@ __global__ void __launch_bounds__(256) gather_keys_kernel(GatherKeysParams p) {
     for (uint32_t i = threadIdx.x; i < r; i += blockDim.x) dst[i] = src[i];
 }
 
-// shard merge: per query concatenate n_lists sorted lists, sort, keep the first `limit`.
+// shard merge: per query concatenate n_lists sorted lists, sort, keep the first `limit`.  The
+// lists are addressed by pointer, so they may live on other GPUs of the process: the leader's
+// merge then reads its peers' result blocks directly over NVLink (peer access enabled).
+static constexpr uint32_t MERGE_MAX_LISTS = 16;
+
 struct MergeParams {
-    const uint32_t* counts;   // list l at counts + l * counts_list_stride: [nq]
-    const uint64_t* keys;     // list l at keys + l * keys_list_stride: [nq][stride]
-    uint64_t counts_list_stride, keys_list_stride;   // in elements
+    const uint32_t* counts[MERGE_MAX_LISTS];   // list l: [nq]
+    const uint64_t* keys[MERGE_MAX_LISTS];     // list l: [nq][stride]
     uint32_t n_lists, nq, stride;
     uint64_t limit;
     uint32_t out_stride;
@@ -352,7 +378,7 @@ __global__ void __launch_bounds__(256) merge_kernel(MergeParams p) {
     if (threadIdx.x == 0) {
         uint32_t t = 0, o = 0;
         for (uint32_t l = 0; l < p.n_lists; ++l) {
-            const uint32_t c = p.counts[l * p.counts_list_stride + q];
+            const uint32_t c = p.counts[l][q];
             if (c >= COUNT_INVALID) o = o > c ? o : c;   // a shard flagged the query
             else t += c < p.stride ? c : p.stride;
         }
@@ -368,9 +394,9 @@ __global__ void __launch_bounds__(256) merge_kernel(MergeParams p) {
     // lists are short; every thread walks the list table
     uint32_t start = 0;
     for (uint32_t l = 0; l < p.n_lists; ++l) {
-        uint32_t c = p.counts[l * p.counts_list_stride + q];
+        uint32_t c = p.counts[l][q];
         if (c > p.stride) c = p.stride;   // (flagged lists returned above)
-        const uint64_t* src = p.keys + l * p.keys_list_stride + static_cast<uint64_t>(q) * p.stride;
+        const uint64_t* src = p.keys[l] + static_cast<uint64_t>(q) * p.stride;
         for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) ms[start + i] = src[i];
         start += c;
     }
@@ -380,7 +406,11 @@ __global__ void __launch_bounds__(256) merge_kernel(MergeParams p) {
     if (total > 1) block_bitonic_sort(ms, np2);
     uint32_t r = total;
     if (p.limit != 0 && r > p.limit) r = static_cast<uint32_t>(p.limit);
-    if (r > p.out_stride) r = p.out_stride;
+    // a merged list longer than the output stride is flagged, never cut silently
+    if (r > p.out_stride) {
+        if (threadIdx.x == 0) p.out_counts[q] = COUNT_OVERFLOW;
+        return;
+    }
     uint64_t* o = p.out_keys + static_cast<uint64_t>(q) * p.out_stride;
     for (uint32_t i = threadIdx.x; i < r; i += blockDim.x) o[i] = ms[i];
     if (threadIdx.x == 0) p.out_counts[q] = r;

@@ -1,14 +1,8 @@
-// drop-in for cobs/query/classic_index/{search_file,mmap_search_file}.hpp of the reference
+// drop-in for cobs/query/classic_index/mmap_search_file.hpp of the reference (17-33)
 #pragma once
-#include <cobs/query/index_file.hpp>
+#include <cobs/query/classic_index/search_file.hpp>
 
 namespace cobs {
-
-class ClassicIndexSearchFile : public IndexSearchFile
-{
-protected:
-    explicit ClassicIndexSearchFile(const fs::path& path) : IndexSearchFile(path, 0) { }
-};
 
 //! a classic index whose matrix is resident in HBM (the reference mmaps it)
 class ClassicIndexMMapSearchFile : public ClassicIndexSearchFile

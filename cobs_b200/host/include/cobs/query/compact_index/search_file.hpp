@@ -1,20 +1,16 @@
-// drop-in for cobs/query/compact_index/{search_file,mmap_search_file}.hpp of the reference
+// drop-in for cobs/query/compact_index/search_file.hpp of the reference (17-39)
 #pragma once
 #include <cobs/query/index_file.hpp>
 
 namespace cobs {
 
-class CompactIndexSearchFile : public IndexSearchFile
+class CompactIndexSearchFile : public HbmIndexSearchFile
 {
 protected:
-    explicit CompactIndexSearchFile(const fs::path& path) : IndexSearchFile(path, 1) { }
-};
+    explicit CompactIndexSearchFile(const fs::path& path) : HbmIndexSearchFile(path, 1) { }
 
-//! a compact index whose pages are resident in HBM (the reference mmaps them)
-class CompactIndexMMapSearchFile : public CompactIndexSearchFile
-{
 public:
-    explicit CompactIndexMMapSearchFile(const fs::path& path) : CompactIndexSearchFile(path) { }
+    virtual ~CompactIndexSearchFile() = default;
 };
 
 } // namespace cobs

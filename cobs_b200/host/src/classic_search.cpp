@@ -12,7 +12,6 @@
 
 #include <algorithm>
 #include <cmath>
-#include <thread>
 #include <tuple>
 
 namespace cobs {
@@ -54,12 +53,23 @@ struct Entry {
     uint32_t doc;
 };
 
-//! runs one packed batch on every shard of one index and appends (score, file, doc) entries
+//! the HBM-resident form of an index file; anything else cannot be searched by this build
+HbmIndexSearchFile& hbm(IndexSearchFile& index) {
+    auto* h = dynamic_cast<HbmIndexSearchFile*>(&index);
+    if (!h)
+        die_with_message("this build searches HBM-resident index files only: wrap custom row "
+                         "sources in cobs::HbmIndexSearchFile(Pages)");
+    return *h;
+}
+
+//! runs one packed batch on one index -- a single GPU handle, or a group of document-axis
+//! shards merged on the leader GPU -- and appends (score, file, doc) entries
 void run_index(
-    IndexSearchFile& index, uint32_t file_num, const std::string& blob,
+    IndexSearchFile& index_file, uint32_t file_num, const std::string& blob,
     const std::vector<uint64_t>& offsets, const std::vector<uint32_t>& ids,
     double threshold, uint64_t limit, std::vector<std::vector<Entry> >& out, Timer& timer) {
     if (ids.empty()) return;
+    HbmIndexSearchFile& index = hbm(index_file);
     // pack the selected queries
     std::string sub;
     std::vector<uint64_t> off(ids.size() + 1, 0);
@@ -67,56 +77,42 @@ void run_index(
         sub.append(blob, offsets[ids[i]], offsets[ids[i] + 1] - offsets[ids[i]]);
         off[i + 1] = sub.size();
     }
-    // one host thread per document shard (= per GPU); each handle has its own stream and buffers
     const auto& shards = index.gpu_shards();
-    struct ShardOut {
-        int rc = COBSGPU_OK;
-        std::string err;
-        std::vector<uint64_t> off;
-        std::vector<uint32_t> doc, score;
-        cobsgpu_timers tm{};
-    };
-    std::vector<ShardOut> outs(shards.size());
-    auto work = [&](size_t s) {
-        ShardOut& o = outs[s];
-        cobsgpu_set_option(shards[s], "timing", 1);
-        cobsgpu_reset_timers(shards[s]);
-        cobsgpu_result res;
-        o.rc = cobsgpu_search_batch(shards[s], sub.data(), off.data(), uint32_t(ids.size()),
-                                    threshold, limit, &res);
-        if (o.rc != COBSGPU_OK) {
-            o.err = cobsgpu_last_error();   // thread-local in the library: read it here
-            return;
-        }
-        o.off.assign(res.offsets, res.offsets + ids.size() + 1);
-        o.doc.assign(res.doc, res.doc + o.off.back());
-        o.score.assign(res.score, res.score + o.off.back());
-        cobsgpu_get_timers(shards[s], &o.tm);
-    };
-    if (shards.size() == 1) {
-        work(0);
+    for (cobsgpu_index* s : shards) {
+        cobsgpu_set_option(s, "timing", 1);
+        cobsgpu_reset_timers(s);
     }
-    else {
-        std::vector<std::thread> threads;
-        for (size_t s = 0; s < shards.size(); ++s) threads.emplace_back(work, s);
-        for (auto& t : threads) t.join();
+    cobsgpu_result res;
+    const int rc = index.gpu_group()
+                   ? cobsgpu_group_search_batch(index.gpu_group(), sub.data(), off.data(),
+                                                uint32_t(ids.size()), threshold, limit, &res)
+                   : cobsgpu_search_batch(shards[0], sub.data(), off.data(), uint32_t(ids.size()),
+                                          threshold, limit, &res);
+    if (rc == COBSGPU_ERR_QUERY_TOO_SHORT) exit_error(cobsgpu_last_error());
+    if (rc == COBSGPU_ERR_INVALID_BASE)
+        die_with_message("Invalid DNA base pair in query string. Only ACGT are allowed.");
+    if (rc != COBSGPU_OK) die_with_message(std::string("GPU search failed: ") + cobsgpu_last_error());
+    for (size_t i = 0; i < ids.size(); ++i) {
+        std::vector<Entry>& dst = out[ids[i]];
+        for (uint64_t e = res.offsets[i]; e < res.offsets[i + 1]; ++e)
+            dst.push_back(Entry { res.score[e], file_num, res.doc[e] });
     }
-    for (ShardOut& o : outs) {
-        if (o.rc == COBSGPU_ERR_QUERY_TOO_SHORT) exit_error(o.err);
-        if (o.rc == COBSGPU_ERR_INVALID_BASE)
-            die_with_message("Invalid DNA base pair in query string. Only ACGT are allowed.");
-        if (o.rc != COBSGPU_OK) die_with_message("GPU search failed: " + o.err);
-        for (size_t i = 0; i < ids.size(); ++i) {
-            std::vector<Entry>& dst = out[ids[i]];
-            for (uint64_t e = o.off[i]; e < o.off[i + 1]; ++e)
-                dst.push_back(Entry { o.score[e], file_num, o.doc[e] });
-        }
-        timer.add("hashes", o.tm.hashes_ms * 1e-3);
-        timer.add("io", (o.tm.h2d_ms + o.tm.d2h_ms) * 1e-3);
-        timer.add("and rows", o.tm.score_ms * 1e-3);   // gather + AND + add are one fused kernel
-        timer.add("add rows", 0.0);
-        timer.add("sort results", o.tm.select_ms * 1e-3);
+    // shards run concurrently: a phase lasts as long as its slowest shard
+    cobsgpu_timers tm{};
+    for (cobsgpu_index* s : shards) {
+        cobsgpu_timers t{};
+        cobsgpu_get_timers(s, &t);
+        tm.hashes_ms = std::max(tm.hashes_ms, t.hashes_ms);
+        tm.score_ms = std::max(tm.score_ms, t.score_ms);
+        tm.select_ms = std::max(tm.select_ms, t.select_ms);
+        tm.h2d_ms = std::max(tm.h2d_ms, t.h2d_ms);
+        tm.d2h_ms = std::max(tm.d2h_ms, t.d2h_ms);
     }
+    timer.add("hashes", tm.hashes_ms * 1e-3);
+    timer.add("io", (tm.h2d_ms + tm.d2h_ms) * 1e-3);
+    timer.add("and rows", tm.score_ms * 1e-3);   // gather + AND + add are one fused kernel
+    timer.add("add rows", 0.0);
+    timer.add("sort results", tm.select_ms * 1e-3);
 }
 
 } // namespace
@@ -159,8 +155,6 @@ void ClassicSearch::search_batch(
         (total_hashes > 1 ? normal : single_hash).push_back(uint32_t(i));
     }
 
-    const bool sharded = std::any_of(index_files_.begin(), index_files_.end(),
-                                     [](auto& f) { return f->gpu_shards().size() > 1; });
     std::vector<std::vector<Entry> > entries(nq);
     for (size_t f = 0; f < index_files_.size(); ++f) {
         // per-index lists are already ordered and cut at `limit`: the global top-k is
@@ -171,7 +165,8 @@ void ClassicSearch::search_batch(
                   entries, timer_);
     }
 
-    const bool merge = index_files_.size() > 1 || sharded;
+    // (a sharded index arrives merged: the group's leader GPU did that)
+    const bool merge = index_files_.size() > 1;
     for (uint32_t i : normal) {
         std::vector<Entry>& e = entries[i];
         if (merge) {

@@ -1,6 +1,6 @@
-// IndexSearchFile: loads an index file into HBM through the C ABI and exposes the reference's
-// getters (cobs/query/index_file.hpp:19-35, classic_index/search_file.cpp:15-23,
-// compact_index/search_file.cpp:15-32).
+// HbmIndexSearchFile: loads an index (file or in-memory pages) into HBM through the C ABI and
+// exposes the reference's getters (cobs/query/index_file.hpp:19-35,
+// classic_index/search_file.cpp:15-23, compact_index/search_file.cpp:15-32).
 #include <cobs/file/file_io_exception.hpp>
 #include <cobs/query/index_file.hpp>
 #include <cobs/settings.hpp>
@@ -13,7 +13,18 @@
 
 namespace cobs {
 
-IndexSearchFile::IndexSearchFile(const fs::path& path, int kind) {
+namespace {
+
+[[noreturn]] void open_failed(int rc) {
+    std::string msg = cobsgpu_last_error();
+    if (rc == COBSGPU_ERR_BAD_FILE) throw FileIOException(msg);
+    if (rc == COBSGPU_ERR_IO) exit_error(msg);   // like open_file(): print + exit
+    throw std::runtime_error("cobs GPU index: " + msg);
+}
+
+} // namespace
+
+HbmIndexSearchFile::HbmIndexSearchFile(const fs::path& path, int kind) {
     // the reference throws FileIOException("invalid file type") when the magic word does not
     // match the class that was asked for (cobs/file/header.hpp:23-29)
     if (kind == 0 && !file_has_header<ClassicIndexHeader>(path))
@@ -21,19 +32,64 @@ IndexSearchFile::IndexSearchFile(const fs::path& path, int kind) {
     if (kind == 1 && !file_has_header<CompactIndexHeader>(path))
         throw FileIOException("invalid file type");
     const unsigned n = gopt_gpus ? gopt_gpus : 1;
-    for (unsigned s = 0; s < n; ++s) {
+    if (n == 1) {
         cobsgpu_index* h = nullptr;
-        int rc = cobsgpu_index_open_file(path.string().c_str(), gopt_gpu_device + int(s), s, n, &h);
-        if (rc != COBSGPU_OK) {
-            for (cobsgpu_index* o : shards_) cobsgpu_index_close(o);
-            shards_.clear();
-            std::string msg = cobsgpu_last_error();
-            if (rc == COBSGPU_ERR_BAD_FILE) throw FileIOException(msg);
-            if (rc == COBSGPU_ERR_IO) exit_error(msg);   // like open_file(): print + exit
-            throw std::runtime_error("cobs GPU index: " + msg);
-        }
+        int rc = cobsgpu_index_open_file(path.string().c_str(), gopt_gpu_device, 0, 1, &h);
+        if (rc != COBSGPU_OK) open_failed(rc);
         shards_.push_back(h);
     }
+    else {
+        // document-axis shards over n GPUs of this process, merged on the leader GPU
+        std::vector<int32_t> devices(n);
+        for (unsigned s = 0; s < n; ++s) devices[s] = gopt_gpu_device + int32_t(s);
+        int rc = cobsgpu_group_open_file(path.string().c_str(), devices.data(), n, &group_);
+        if (rc != COBSGPU_OK) open_failed(rc);
+        for (unsigned s = 0; s < n; ++s) shards_.push_back(cobsgpu_group_shard(group_, s));
+    }
+    read_geometry();
+    cobsgpu_index_info info;
+    cobsgpu_index_get_info(shards_[0], &info);
+    file_names_.resize(info.n_docs);
+    for (uint32_t d = 0; d < info.n_docs; ++d) file_names_[d] = cobsgpu_index_doc_name(shards_[0], d);
+}
+
+HbmIndexSearchFile::HbmIndexSearchFile(const Pages& p) {
+    if (p.signature_sizes.empty() || p.signature_sizes.size() != p.page_data.size())
+        throw std::runtime_error("HbmIndexSearchFile: one signature size and one data pointer per page");
+    cobsgpu_index_desc d;
+    std::memset(&d, 0, sizeof(d));
+    d.struct_size = sizeof(d);
+    d.kind = p.compact ? COBSGPU_KIND_COMPACT : COBSGPU_KIND_CLASSIC;
+    d.term_size = p.term_size;
+    d.canonicalize = p.canonicalize;
+    d.num_hashes = uint32_t(p.num_hashes);
+    d.n_docs = uint32_t(p.file_names.size());
+    d.n_pages = uint32_t(p.signature_sizes.size());
+    d.page_size = p.compact ? p.page_size : (p.file_names.size() + 7) / 8;
+    d.signature_sizes = p.signature_sizes.data();
+    d.page_data = p.page_data.data();
+    d.device = gopt_gpu_device;
+    d.shard_index = 0;
+    d.shard_count = 1;
+    const unsigned n = gopt_gpus ? gopt_gpus : 1;
+    if (n == 1) {
+        cobsgpu_index* h = nullptr;
+        int rc = cobsgpu_index_open(&d, &h);
+        if (rc != COBSGPU_OK) open_failed(rc);
+        shards_.push_back(h);
+    }
+    else {
+        std::vector<int32_t> devices(n);
+        for (unsigned s = 0; s < n; ++s) devices[s] = gopt_gpu_device + int32_t(s);
+        int rc = cobsgpu_group_open(&d, devices.data(), n, &group_);
+        if (rc != COBSGPU_OK) open_failed(rc);
+        for (unsigned s = 0; s < n; ++s) shards_.push_back(cobsgpu_group_shard(group_, s));
+    }
+    read_geometry();
+    file_names_ = p.file_names;
+}
+
+void HbmIndexSearchFile::read_geometry() {
     cobsgpu_index_info info;
     cobsgpu_index_get_info(shards_[0], &info);
     term_size_ = info.term_size;
@@ -44,18 +100,18 @@ IndexSearchFile::IndexSearchFile(const fs::path& path, int kind) {
     counts_size_ = info.counts_size;
     for (uint32_t p = 0; p < info.n_pages; ++p)
         signature_sizes_.push_back(cobsgpu_index_signature_size(shards_[0], p));
-    file_names_.resize(info.n_docs);
-    for (uint32_t d = 0; d < info.n_docs; ++d) file_names_[d] = cobsgpu_index_doc_name(shards_[0], d);
 }
 
-IndexSearchFile::~IndexSearchFile() {
-    for (cobsgpu_index* h : shards_) cobsgpu_index_close(h);
+HbmIndexSearchFile::~HbmIndexSearchFile() {
+    if (group_) cobsgpu_group_close(group_);   // owns its shards
+    else
+        for (cobsgpu_index* h : shards_) cobsgpu_index_close(h);
 }
 
 //! Source-compatibility shim: copies `size` bytes starting at byte `begin` of the rows selected
 //! by the raw hashes back from HBM, laid out like the reference's rows buffer.  Classic
 //! indices only (the modulo is per page for compact ones); not on the search path.
-void IndexSearchFile::read_from_disk(
+void HbmIndexSearchFile::read_from_disk(
     const std::vector<size_t>& hashes, uint8_t* rows,
     size_t begin, size_t size, size_t buffer_size) {
     if (page_size_ != 1 || shards_.size() != 1)

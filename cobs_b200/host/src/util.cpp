@@ -10,6 +10,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <mutex>
 #include <thread>
 
 namespace cobs {
@@ -99,7 +100,11 @@ void Timer::add(const char* timer, double seconds) {
     total_ += seconds;
 }
 
+//! several threads may fold their timers into a shared one (reference: timer.cpp:67-75)
+static std::mutex s_timer_add_mutex;
+
 Timer& Timer::operator += (const Timer& b) {
+    std::unique_lock<std::mutex> lock(s_timer_add_mutex);
     for (const Entry& t : b.timers_) find_or_create(t.name.c_str()).seconds += t.seconds;
     total_ += b.total_;
     return *this;

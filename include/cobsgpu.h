@@ -265,6 +265,33 @@ int cobsgpu_merge_device(int device, uint32_t n_lists, uint32_t nq,
                          uint32_t out_per_query, uint32_t* d_out_counts,
                          uint64_t* d_out_keys, void* stream);
 
+/*
+ * Multi-GPU inside ONE process ("a single process with one stream per GPU
+ * is sufficient on one NVSwitch host"): a group holds the n_devices document-axis shards of one
+ * index, shard g on devices[g] (classic: contiguous column ranges; compact: whole pages).
+ * cobsgpu_group_search_batch runs K1-K3 on every shard concurrently, then the leader (shard 0)
+ * merges the shards' fixed-size result blocks [nq][k] with ONE kernel that reads them straight
+ * out of the peers' HBM over NVLink (peer access; staged copies when the devices cannot map
+ * each other) and returns one ordered list per query -- same semantics and result layout as
+ * cobsgpu_search_batch on an unsharded index.  A query that overflows a shard's candidate
+ * slots is redone on every shard's exhaustive path and merged on the host: nothing is dropped.
+ * replaces: the column-batch parallel_for of search_index_file
+ * (cobs/query/classic_search.cpp:355-400) spread over GPUs instead of threads.
+ */
+typedef struct cobsgpu_group cobsgpu_group;
+int cobsgpu_group_open_file(const char* path, const int32_t* devices, uint32_t n_devices,
+                            cobsgpu_group** out);
+/* desc->device / shard_index / shard_count are ignored (set per shard) */
+int cobsgpu_group_open(const cobsgpu_index_desc* desc, const int32_t* devices, uint32_t n_devices,
+                       cobsgpu_group** out);
+void cobsgpu_group_close(cobsgpu_group* grp);
+uint32_t cobsgpu_group_size(const cobsgpu_group* grp);
+/* shard i of the group (borrowed): geometry, document names, timers, options */
+cobsgpu_index* cobsgpu_group_shard(cobsgpu_group* grp, uint32_t i);
+int cobsgpu_group_search_batch(cobsgpu_group* grp, const char* queries, const uint64_t* offsets,
+                               uint32_t nq, double threshold, uint64_t num_results,
+                               cobsgpu_result* out);
+
 int cobsgpu_get_timers(const cobsgpu_index* idx, cobsgpu_timers* out);
 int cobsgpu_reset_timers(cobsgpu_index* idx);
 

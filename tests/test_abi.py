@@ -22,7 +22,7 @@ def header_symbols():
 def test_library_exports_every_declared_symbol():
     L = cobs_b200.lib()
     names = header_symbols()
-    assert len(names) == 22
+    assert len(names) == 28
     for n in names:
         assert hasattr(L, n), n
     # and the ctypes table covers the header exactly
