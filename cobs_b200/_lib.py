@@ -87,6 +87,10 @@ class IndexInfo(C.Structure):
         ("shard_doc_end", C.c_uint32),
         ("hbm_bytes", C.c_uint64),
         ("bytes_per_kmer", C.c_uint64),
+        ("load_seconds", C.c_double),
+        ("load_bytes", C.c_uint64),
+        ("load_threads", C.c_uint32),
+        ("reserved", C.c_uint32),
     ]
 
 

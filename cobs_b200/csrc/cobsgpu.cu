@@ -13,6 +13,8 @@
 #include "../../include/cobsgpu.h"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstdio>
@@ -21,6 +23,7 @@
 #include <cstring>
 #include <functional>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -266,6 +269,11 @@ struct cobsgpu_index {
     unsigned long long* d_work = nullptr;
     uint32_t work_slot = 0;
 
+    // loader statistics of the last open (matrix bytes read from the source, wall seconds)
+    double load_seconds = 0;
+    uint64_t load_bytes = 0;
+    uint32_t load_threads = 0;
+
     // device properties
     int sm_count = 0;
     size_t smem_optin = 0;
@@ -278,7 +286,9 @@ struct cobsgpu_index {
 
     // execution state: three streams so that consecutive batches overlap -- s_in uploads the
     // queries + metadata and runs K1, `stream` (main) runs K2 + K3, s_out copies results back
-    cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
+    // (s_fix: follow-up copies of a collect, which must not queue behind later batches' downloads)
+    cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr, s_fix = nullptr;
+    uint64_t spec_hint = 0;               // keys the last collected batch returned
     static constexpr int N_SLOTS = 4;     // batches in flight (submit/collect tickets)
     Slot slots[N_SLOTS];
     Slot aux;                             // workspace of the exhaustive passes / cobsgpu_scores
@@ -307,10 +317,11 @@ struct cobsgpu_index {
     };
     std::vector<Ev> pending;
     std::vector<cudaEvent_t> ev_pool;
+    cudaEvent_t trace_base = nullptr;
 
     ~cobsgpu_index() {
         cudaSetDevice(device);
-        for (cudaStream_t st : { s_in, stream, s_out })
+        for (cudaStream_t st : { s_in, stream, s_out, s_fix })
             if (st) cudaStreamSynchronize(st);
         for (auto& e : pending) {
             cudaEventDestroy(e.a);
@@ -324,7 +335,7 @@ struct cobsgpu_index {
         if (d_tiles) cudaFree(d_tiles);
         if (d_seg) cudaFree(d_seg);
         if (d_work) cudaFree(d_work);
-        for (cudaStream_t st : { s_in, stream, s_out })
+        for (cudaStream_t st : { s_in, stream, s_out, s_fix })
             if (st) cudaStreamDestroy(st);
     }
 };
@@ -362,10 +373,29 @@ struct PhaseScope {
     }
 };
 
-void resolve_timers(cobsgpu_index* ix) {
+void resolve_timers(cobsgpu_index* ix, bool wait = true) {
+    // experiments only: COBSGPU_TRACE=1 prints every phase's start/end on the device timeline
+    static const bool trace = std::getenv("COBSGPU_TRACE") != nullptr;
+    static const char* names[] = { "h2d", "hash", "score", "select", "d2h" };
+    std::vector<cobsgpu_index::Ev> later;
     for (auto& e : ix->pending) {
         float ms = 0;
+        // (a collect in the middle of a pipeline must not wait for the batches behind it)
+        if (!wait && cudaEventQuery(e.b) != cudaSuccess) {
+            cudaGetLastError();
+            later.push_back(e);
+            continue;
+        }
         if (cudaEventSynchronize(e.b) == cudaSuccess && cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) {
+            if (trace) {
+                if (!ix->trace_base) {
+                    ix->trace_base = e.a;   // (kept out of the pool below)
+                }
+                float t0 = 0, t1 = 0;
+                cudaEventElapsedTime(&t0, ix->trace_base, e.a);
+                cudaEventElapsedTime(&t1, ix->trace_base, e.b);
+                std::fprintf(stderr, "TRACE %-6s %10.3f %10.3f us\n", names[e.phase], 1e3 * t0, 1e3 * t1);
+            }
             switch (e.phase) {
             case PH_H2D: ix->tm.h2d_ms += ms; break;
             case PH_HASH: ix->tm.hashes_ms += ms; break;
@@ -374,10 +404,10 @@ void resolve_timers(cobsgpu_index* ix) {
             case PH_D2H: ix->tm.d2h_ms += ms; break;
             }
         }
-        ix->ev_pool.push_back(e.a);
+        if (e.a != ix->trace_base) ix->ev_pool.push_back(e.a);
         ix->ev_pool.push_back(e.b);
     }
-    ix->pending.clear();
+    ix->pending.swap(later);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -519,30 +549,145 @@ void build_tiles(cobsgpu_index* ix) {
 }
 
 // Fills dst with source rows [row0, row0 + nrows) of GLOBAL page `page`, full source rows of
-// page_size_src bytes each (memcpy from host pointers, or pread from the index file).
+// page_size_src bytes each (memcpy from host pointers, or pread from the index file).  Called
+// concurrently from several loader threads.
 using RowReader = std::function<void(uint32_t page, uint64_t row0, uint64_t nrows, uint8_t* dst)>;
 
-// Streams one page into HBM: the host thread reads chunk i+1 into one pinned staging buffer
-// while the DMA engine re-pitches chunk i out of the other (source row stride page_size ->
-// device pitch, only this shard's column bytes).  The analogue of the reference's
-// --load-complete read loop (cobs/util/query.cpp:56-86), with HBM as the destination.
-void stream_page(cobsgpu_index* ix, const LocalPage& lp, const RowReader& read, PinBuf (&stage)[2],
-                 cudaEvent_t (&ev)[2], int& slot) {
+// Streams the pages of this shard into HBM: the analogue of the reference's --load-complete read
+// loop (cobs/util/query.cpp:56-86), with HBM as the destination.  The matrix is cut into chunks
+// of whole rows; LOADER_THREADS host threads each own two pinned staging buffers and a stream and
+// take chunks round-robin: pread (page-cache copy, the slow part: a few GB/s per thread) into one
+// buffer while the DMA engine re-pitches the previous chunk out of the other (source row stride
+// page_size -> device pitch, only this shard's column bytes).  Threads never wait for each other,
+// so the copies of all of them keep the PCIe link busy.  Only the padding columns are zeroed.
+// Pinned staging buffers outlive a load: page-locking memory costs ~0.7 s per GB, far more than
+// copying through it, so the buffers are kept for the next index (or the next shard) to load.
+struct StagePool {
+    std::mutex m;
+    std::vector<PinBuf*> idle;
+    PinBuf* take(size_t bytes) {
+        {
+            std::lock_guard<std::mutex> lock(m);
+            for (size_t i = 0; i < idle.size(); ++i)
+                if (idle[i]->cap >= bytes) {
+                    PinBuf* b = idle[i];
+                    idle.erase(idle.begin() + i);
+                    return b;
+                }
+        }
+        std::unique_ptr<PinBuf> b(new PinBuf);
+        b->reserve(bytes);
+        return b.release();
+    }
+    void give(PinBuf* b) {
+        std::lock_guard<std::mutex> lock(m);
+        if (idle.size() < 64) idle.push_back(b);
+        else delete b;
+    }
+};
+StagePool g_stage_pool;
+
+struct LoaderStats {
+    double seconds = 0;
+    uint64_t bytes = 0;
+    uint32_t threads = 0;
+};
+
+void stream_pages(cobsgpu_index* ix, const RowReader& read, LoaderStats* stats) {
     const uint64_t ps = ix->page_size_src;
-    const uint64_t target = 64ull << 20;
+    struct Chunk {
+        const LocalPage* lp;
+        uint64_t row0, nrows;
+    };
+    std::vector<Chunk> chunks;
+    uint64_t target = 4ull << 20;
+    if (const char* e = std::getenv("COBSGPU_LOADER_CHUNK_MB"))
+        target = static_cast<uint64_t>(std::max(1, std::atoi(e))) << 20;
     const uint64_t chunk_rows = std::max<uint64_t>(1, target / std::max<uint64_t>(1, ps));
-    CK(cudaMemsetAsync(lp.d_base, 0, lp.sig * lp.pitch, ix->stream));   // zero padding
-    for (uint64_t r = 0; r < lp.sig; r += chunk_rows) {
-        const uint64_t nr = std::min<uint64_t>(chunk_rows, lp.sig - r);
-        stage[slot].ensure(nr * ps);
-        if (!ev[slot]) CK(cudaEventCreateWithFlags(&ev[slot], cudaEventDisableTiming));
-        else CK(cudaEventSynchronize(ev[slot]));   // DMA out of this buffer has finished
-        uint8_t* buf = stage[slot].as<uint8_t>();
-        read(lp.global_page, r, nr, buf);
-        CK(cudaMemcpy2DAsync(lp.d_base + r * lp.pitch, lp.pitch, buf + lp.byte_begin, ps,
-                             lp.row_bytes, nr, cudaMemcpyHostToDevice, ix->stream));
-        CK(cudaEventRecord(ev[slot], ix->stream));
-        slot ^= 1;
+    uint64_t total = 0;
+    for (const LocalPage& lp : ix->pages) {
+        if (lp.pitch > lp.row_bytes)   // zero padding columns (everything else is overwritten)
+            CK(cudaMemset2DAsync(lp.d_base + lp.row_bytes, lp.pitch, 0, lp.pitch - lp.row_bytes, lp.sig,
+                                 ix->stream));
+        for (uint64_t r = 0; r < lp.sig; r += chunk_rows)
+            chunks.push_back({ &lp, r, std::min<uint64_t>(chunk_rows, lp.sig - r) });
+        total += lp.sig * ps;
+    }
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 4;
+    // measured on a 16-vCPU host: 8 threads read ~45 GB/s out of the page cache, more only fight
+    // over memory bandwidth with the DMA engine
+    uint32_t nthreads = static_cast<uint32_t>(std::min<size_t>(std::max(4u, std::min(hw / 2, 16u)), chunks.size()));
+    if (const char* e = std::getenv("COBSGPU_LOADER_THREADS"))
+        nthreads = static_cast<uint32_t>(std::max(1, std::min(64, std::atoi(e))));
+    nthreads = std::max<uint32_t>(1, std::min<uint32_t>(nthreads, static_cast<uint32_t>(std::max<size_t>(chunks.size(), 1))));
+    const size_t buf_bytes = static_cast<size_t>(chunk_rows * ps);
+    // experiments only: COBSGPU_LOADER_MODE=read skips the DMA, =dma skips the reads
+    int dbg_mode = 0;
+    if (const char* e = std::getenv("COBSGPU_LOADER_MODE"))
+        dbg_mode = std::strcmp(e, "read") == 0 ? 1 : (std::strcmp(e, "dma") == 0 ? 2 : 0);
+    std::atomic<size_t> next{ 0 };
+    std::vector<Err> errors(nthreads, Err{ COBSGPU_OK, "" });
+    const auto t0 = std::chrono::steady_clock::now();
+    auto worker = [&](uint32_t t) {
+        try {
+            CK(cudaSetDevice(ix->device));
+            PinBuf* stage[2] = { nullptr, nullptr };
+            cudaEvent_t ev[2] = { nullptr, nullptr };
+            cudaStream_t st = nullptr;
+            CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+            struct Guard {
+                cudaEvent_t (&ev)[2];
+                cudaStream_t& st;
+                PinBuf* (&stage)[2];
+                ~Guard() {
+                    if (st) {
+                        cudaStreamSynchronize(st);
+                        cudaStreamDestroy(st);
+                    }
+                    for (cudaEvent_t e : ev)
+                        if (e) cudaEventDestroy(e);
+                    for (PinBuf* b : stage)
+                        if (b) g_stage_pool.give(b);
+                }
+            } guard{ ev, st, stage };
+            int slot = 0;
+            for (;;) {
+                const size_t c = next.fetch_add(1);
+                if (c >= chunks.size()) break;
+                const Chunk& ch = chunks[c];
+                const LocalPage& lp = *ch.lp;
+                if (!stage[slot]) stage[slot] = g_stage_pool.take(buf_bytes);
+                if (!ev[slot]) CK(cudaEventCreateWithFlags(&ev[slot], cudaEventDisableTiming));
+                else CK(cudaEventSynchronize(ev[slot]));   // DMA out of this buffer has finished
+                uint8_t* buf = stage[slot]->as<uint8_t>();
+                if (dbg_mode != 2) read(lp.global_page, ch.row0, ch.nrows, buf);
+                if (dbg_mode != 1)
+                    CK(cudaMemcpy2DAsync(lp.d_base + ch.row0 * lp.pitch, lp.pitch, buf + lp.byte_begin, ps,
+                                         lp.row_bytes, ch.nrows, cudaMemcpyHostToDevice, st));
+                CK(cudaEventRecord(ev[slot], st));
+                slot ^= 1;
+            }
+            CK(cudaStreamSynchronize(st));
+        } catch (const Err& e) {
+            errors[t] = e;
+        }
+    };
+    if (nthreads == 1) {
+        worker(0);
+    } else {
+        std::vector<std::thread> th;
+        for (uint32_t t = 0; t < nthreads; ++t) th.emplace_back(worker, t);
+        for (auto& t : th) t.join();
+    }
+    CK(cudaSetDevice(ix->device));
+    for (const Err& e : errors)
+        if (e.code != COBSGPU_OK) throw e;
+    CK(cudaStreamSynchronize(ix->stream));
+    if (stats) {
+        stats->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        stats->bytes = total;
+        stats->threads = nthreads;
     }
 }
 
@@ -576,6 +721,7 @@ void open_common(cobsgpu_index* ix, const std::vector<uint64_t>& sig,
         CK(cudaStreamCreateWithPriority(&ix->stream, cudaStreamNonBlocking, lo_p));
         CK(cudaStreamCreateWithPriority(&ix->s_in, cudaStreamNonBlocking, hi_p));
         CK(cudaStreamCreateWithPriority(&ix->s_out, cudaStreamNonBlocking, hi_p));
+        CK(cudaStreamCreateWithPriority(&ix->s_fix, cudaStreamNonBlocking, hi_p));
     }
     if (ix->hbm_bytes) {
         CK(cudaMalloc(reinterpret_cast<void**>(&ix->d_arena), ix->hbm_bytes));
@@ -584,19 +730,16 @@ void open_common(cobsgpu_index* ix, const std::vector<uint64_t>& sig,
             lp.d_base = ix->d_arena + off;
             off += round_up<uint64_t>(lp.sig * lp.pitch, 256);
         }
-        PinBuf stage[2];
-        cudaEvent_t ev[2] = { nullptr, nullptr };
-        int slot = 0;
-        struct EvGuard {
-            cudaEvent_t (&ev)[2];
-            ~EvGuard() {
-                for (cudaEvent_t e : ev)
-                    if (e) cudaEventDestroy(e);
-            }
-        } guard{ ev };
+        if (reader) {
+            LoaderStats ls;
+            stream_pages(ix, *reader, &ls);
+            ix->load_seconds = ls.seconds;
+            ix->load_bytes = ls.bytes;
+            ix->load_threads = ls.threads;
+        }
         for (auto& lp : ix->pages) {
             if (reader) {
-                stream_page(ix, lp, *reader, stage, ev, slot);
+                continue;
             } else if (zero_fill) {
                 CK(cudaMemsetAsync(lp.d_base, 0, lp.sig * lp.pitch, ix->stream));
             } else {
@@ -1190,7 +1333,9 @@ Slot& submit_batch(cobsgpu_index* ix, const char* queries, const uint64_t* offse
     CK(cudaEventRecord(sl.ev(sl.ev_main), st));
     // ONE device-to-host copy in the common case: the header and the first spec_keys keys
     const uint64_t max_keys = (ob - sl.out_keys) / 8;
-    sl.spec_keys = std::min<uint64_t>(max_keys, std::max<uint64_t>(8192, 8ull * n_main));
+    // (sized from what the previous batch returned, with headroom)
+    sl.spec_keys = std::min<uint64_t>(
+        max_keys, std::max<uint64_t>(std::max<uint64_t>(8192, 8ull * n_main), ix->spec_hint + ix->spec_hint / 4));
     sl.h_out.ensure(sl.out_keys + sl.spec_keys * 8);
     CK(cudaStreamWaitEvent(ix->s_out, sl.ev_main, 0));
     {
@@ -1235,17 +1380,18 @@ void collect_batch(cobsgpu_index* ix, Slot& sl) {
         const uint64_t* off = reinterpret_cast<const uint64_t*>(h + sl.out_off);
         const uint32_t* cc = reinterpret_cast<const uint32_t*>(h + sl.out_cc);
         const uint64_t total = off[n_main];
+        ix->spec_hint = total;
         if (total > sl.spec_keys) {
             // more results than the speculative copy carried: fetch the rest
             sl.h_out.ensure_keep(sl.out_keys + total * 8, sl.out_keys + sl.spec_keys * 8);
             h = sl.h_out.as<char>();
             off = reinterpret_cast<const uint64_t*>(h + sl.out_off);
             cc = reinterpret_cast<const uint32_t*>(h + sl.out_cc);
-            PhaseScope ps(ix, PH_D2H, ix->s_out);
+            // (on its own stream: s_out already holds the downloads of the batches behind this one)
             CK(cudaMemcpyAsync(sl.h_out.as<char>() + sl.out_keys + sl.spec_keys * 8,
                                sl.o_keys() + sl.spec_keys, (total - sl.spec_keys) * 8,
-                               cudaMemcpyDeviceToHost, ix->s_out));
-            CK(cudaStreamSynchronize(ix->s_out));
+                               cudaMemcpyDeviceToHost, ix->s_fix));
+            CK(cudaStreamSynchronize(ix->s_fix));
         }
         lists.emplace_back();
         HostList& L = lists.back();
@@ -1309,7 +1455,7 @@ void check_idle(const cobsgpu_index* ix) {
 }
 
 void drop_tickets(cobsgpu_index* ix) {
-    for (cudaStream_t st : { ix->s_in, ix->stream, ix->s_out })
+    for (cudaStream_t st : { ix->s_in, ix->stream, ix->s_out, ix->s_fix })
         if (st) cudaStreamSynchronize(st);
     for (Slot& sl : ix->slots) sl.busy = false;
 }
@@ -1528,8 +1674,9 @@ GSlot& group_submit(cobsgpu_group* grp, const char* queries, const uint64_t* off
                      gsl.out_stride, st);
     CK(cudaMemcpyAsync(ls.o_cc(), gsl.d_mcount.p, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToDevice, st));
     CK(cudaEventRecord(ls.ev(ls.ev_main), st));
-    gsl.spec_keys = std::min<uint64_t>(static_cast<uint64_t>(nq) * gsl.out_stride,
-                                       std::max<uint64_t>(8192, 8ull * nq));
+    gsl.spec_keys = std::min<uint64_t>(
+        static_cast<uint64_t>(nq) * gsl.out_stride,
+        std::max<uint64_t>(std::max<uint64_t>(8192, 8ull * nq), lead->spec_hint + lead->spec_hint / 4));
     ls.h_out.ensure(ls.out_keys + gsl.spec_keys * 8);
     CK(cudaStreamWaitEvent(lead->s_out, ls.ev_main, 0));
     {
@@ -1581,14 +1728,15 @@ void group_collect(cobsgpu_group* grp, GSlot& gsl) {
         if (flags[0] != FLAG_CLEAR) throw_bad_base(gsl.q0 + static_cast<uint32_t>(flags[0]));
         const uint64_t* off = reinterpret_cast<const uint64_t*>(h + ls.out_off);
         const uint64_t total = off[nq];
+        lead->spec_hint = total;
         if (total > gsl.spec_keys) {
             ls.h_out.ensure_keep(ls.out_keys + total * 8, ls.out_keys + gsl.spec_keys * 8);
             h = ls.h_out.as<char>();
             off = reinterpret_cast<const uint64_t*>(h + ls.out_off);
             CK(cudaMemcpyAsync(ls.h_out.as<char>() + ls.out_keys + gsl.spec_keys * 8,
                                ls.o_keys() + gsl.spec_keys, (total - gsl.spec_keys) * 8,
-                               cudaMemcpyDeviceToHost, lead->s_out));
-            CK(cudaStreamSynchronize(lead->s_out));
+                               cudaMemcpyDeviceToHost, lead->s_fix));
+            CK(cudaStreamSynchronize(lead->s_fix));
         }
         const uint32_t* cc = reinterpret_cast<const uint32_t*>(h + ls.out_cc);
         for (uint32_t i = 0; i < nq; ++i)
@@ -1922,6 +2070,10 @@ int cobsgpu_index_get_info(const cobsgpu_index* ix, cobsgpu_index_info* o) {
         o->shard_doc_end = ix->shard_doc_end;
         o->hbm_bytes = ix->hbm_bytes;
         o->bytes_per_kmer = ix->bytes_per_kmer;
+        o->load_seconds = ix->load_seconds;
+        o->load_bytes = ix->load_bytes;
+        o->load_threads = ix->load_threads;
+        o->reserved = 0;
     });
 }
 
@@ -2114,7 +2266,7 @@ int cobsgpu_collect(cobsgpu_index* ix, cobsgpu_ticket ticket, cobsgpu_result* ou
         for (Slot& sl : ix->slots) {
             if (!sl.busy || sl.ticket != ticket) continue;
             collect_batch(ix, sl);
-            resolve_timers(ix);
+            resolve_timers(ix, false);
             out->offsets = sl.r_off.data();
             out->doc = sl.r_doc.data();
             out->score = sl.r_score.data();

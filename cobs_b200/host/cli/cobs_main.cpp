@@ -9,6 +9,8 @@
 #include <cobs/util/error_handling.hpp>
 #include <cobs/util/file.hpp>
 
+#include <cobsgpu.h>
+
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
@@ -263,7 +265,7 @@ int main(int argc, char** argv) {
         if (tool == "query") return query(argc - 1, argv + 1);
         if (tool == "benchmark-fpr") return benchmark_fpr(argc - 1, argv + 1);
         if (tool == "version") {
-            std::cout << "COBS B200 query path, C ABI version 1" << std::endl;
+            std::cout << "COBS B200 query path, C ABI version " << cobsgpu_version() << std::endl;
             return 0;
         }
     }

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define COBSGPU_VERSION 1
+#define COBSGPU_VERSION 2
 
 /* status codes */
 #define COBSGPU_OK 0
@@ -100,6 +100,13 @@ typedef struct cobsgpu_index_info {
     uint64_t hbm_bytes;         /* bytes of signature matrix resident on the device */
     uint64_t bytes_per_kmer;    /* algorithmic bytes per query k-mer for THIS shard:
                                    h * (unpadded row bytes held) */
+    /* loader statistics of a file / host-array open (0 for synthetic indices): matrix bytes read
+     * from the source, wall-clock seconds from the first read to the last byte in HBM, host
+     * threads used (replaces the progress lines of cobs/util/query.cpp:56-86) */
+    double load_seconds;
+    uint64_t load_bytes;
+    uint32_t load_threads;
+    uint32_t reserved;
 } cobsgpu_index_info;
 
 /* Result lists of one batch, CSR.  Query q owns entries [offsets[q], offsets[q+1]),

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, n), n
     # and the ctypes table covers the header exactly
     assert sorted(_lib.SYMBOLS) == names
-    assert L.cobsgpu_version() == 1
+    assert L.cobsgpu_version() == 2
 
 
 def test_exported_symbols_are_plain_c():
@@ -42,7 +42,7 @@ def test_exported_symbols_are_plain_c():
 def test_struct_layouts_match_header():
     # sizes implied by include/cobsgpu.h (natural alignment, 64-bit)
     assert C.sizeof(_lib.IndexDesc) == 80
-    assert C.sizeof(_lib.IndexInfo) == 80
+    assert C.sizeof(_lib.IndexInfo) == 104
     assert C.sizeof(_lib.Result) == 24
     assert C.sizeof(_lib.Timers) == 72
 

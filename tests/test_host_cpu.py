@@ -43,7 +43,7 @@ def test_usage_and_version():
     r = subprocess.run([COBS], stdout=subprocess.PIPE, text=True)
     assert r.returncode == 0 and "query" in r.stdout
     r = subprocess.run([COBS, "version"], stdout=subprocess.PIPE, text=True)
-    assert "C ABI version 1" in r.stdout
+    assert "C ABI version 2" in r.stdout
     r = subprocess.run([COBS, "query", "--help"], stdout=subprocess.PIPE, text=True)
     for flag in ("--index", "--file", "--threshold", "--limit", "--load-complete", "--threads"):
         assert flag in r.stdout       # the reference's flags (src/cobs.cpp:474-505)
