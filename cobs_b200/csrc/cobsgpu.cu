@@ -30,6 +30,7 @@
 
 #include "common.cuh"
 #include "construct.cuh"
+#include "densesort.cuh"
 #include "fill.cuh"
 #include "hash.cuh"
 #include "index_file.hpp"
@@ -165,6 +166,7 @@ struct Slot {
     // device: d_meta = [flags 2 x int | bad nq x u32 | qoff | koff | thr] in one block,
     // d_out = [flags 2 x int | offsets (nq+1) x u64 | cand_count nq x u32 | keys ...]
     DevBuf d_queries, d_meta, d_hashes, d_cand, d_scratch, d_res_count, d_out, d_qlist, d_dense;
+    DevBuf d_hist, d_total;              // counting sort of the exhaustive lists (aux slot only)
     size_t meta_qoff = 0, meta_koff = 0, meta_thr = 0, meta_bad = 0;
     size_t out_off = 0, out_cc = 0, out_keys = 0;
     const char* dev_queries = nullptr;
@@ -781,6 +783,7 @@ ScoreFn pick_score(uint32_t h, int mode, bool lng) {
     case MODE_CAND: return lng ? pick_h<MODE_CAND, 16>(h) : pick_h<MODE_CAND, 8>(h);
     case MODE_TOPK: return lng ? pick_h<MODE_TOPK, 16>(h) : pick_h<MODE_TOPK, 8>(h);
     case MODE_DENSE8: return pick_h<MODE_DENSE8, 8>(h);
+    case MODE_DENSE16: return pick_h<MODE_DENSE16, 16>(h);
     default: return pick_h<MODE_DENSE32, 8>(h);
     }
 }
@@ -791,6 +794,7 @@ void launch_score(cobsgpu_index* ix, ScoreParams sp, int mode, bool lng, cudaStr
     ScoreFn fn = pick_score(h, mode, lng);
     const int threads = static_cast<int>((ix->ncw + 1) * 32);
     if (mode == MODE_DENSE8 || mode == MODE_DENSE32) lng = false;
+    if (mode == MODE_DENSE16) lng = true;
     cobsgpu_index::ScoreCfg& cfg = ix->score_cfg[mode][lng ? 1 : 0];
     if (!cfg.valid) {
         const uint32_t W = ix->ncw * 512;
@@ -1160,8 +1164,83 @@ const uint32_t* upload_qlist(Slot& work, const std::vector<uint32_t>& ids, size_
     return work.d_qlist.as<uint32_t>();
 }
 
+// One sub-batch of the exhaustive path for queries of at most 65 535 k-mers: K2 stores one count
+// per document (DENSE8 / DENSE16), then a stable multi-CTA counting sort on the score
+// (densesort.cuh) writes the ordered keys straight into the CSR area of work.d_out.
+void exhaustive_dense(cobsgpu_index* ix, const Slot& src, Slot& work, const uint32_t* d_ql,
+                      uint32_t n, uint32_t max_T, uint64_t limit, cudaStream_t st) {
+    const bool two = max_T > MAX_T_SHORT;
+    const uint32_t cap = std::max<uint32_t>(ix->shard_real_docs, 1);
+    const size_t esz = two ? 2 : 1;
+    const uint32_t dense_cols = static_cast<uint32_t>(ix->dense_pitch);
+    const uint32_t n_chunks = div_ceil<uint32_t>(std::max<uint32_t>(dense_cols, cap), DS_CHUNK);
+    work.d_dense.ensure(static_cast<uint64_t>(n) * ix->dense_pitch * esz);
+    work.d_hist.ensure(static_cast<uint64_t>(n) * n_chunks * 256 * 4);
+    work.d_total.ensure(static_cast<size_t>(n) * 8);
+    uint32_t* total1 = work.d_total.as<uint32_t>();
+    uint32_t* total2 = total1 + n;
+    CK(cudaMemsetAsync(work.d_dense.p, 0, static_cast<uint64_t>(n) * ix->dense_pitch * esz, st));
+    CK(cudaMemsetAsync(work.o_cc(), 0, static_cast<size_t>(n) * 4, st));   // (no candidate slots here)
+    ScoreParams sp = base_params(ix, src, d_ql, n);
+    sp.dense8 = work.d_dense.as<uint8_t>();
+    sp.dense16 = work.d_dense.as<uint16_t>();
+    launch_score(ix, sp, two ? MODE_DENSE16 : MODE_DENSE8, two, st);
+
+    PhaseScope ps(ix, PH_SELECT, st);
+    const uint32_t np = static_cast<uint32_t>(ix->pages.size());
+    DenseSortParams dp{};
+    dp.dense8 = sp.dense8;
+    dp.dense16 = sp.dense16;
+    dp.dense_pitch = ix->dense_pitch;
+    dp.dense_cols = dense_cols;
+    dp.qlist = d_ql;
+    dp.thr = src.d_thr();
+    dp.seg_dense_off = ix->d_seg;
+    dp.seg_n_real = ix->d_seg + np;
+    dp.seg_doc_base = ix->d_seg + 2 * np;
+    dp.n_seg = np;
+    dp.cap = cap;
+    dp.n_chunks = n_chunks;
+    dp.hist = work.d_hist.as<uint32_t>();
+    dp.limit = limit;
+    const dim3 grid(n_chunks, n);
+    auto final_pass = [&](uint32_t* totals) {
+        // slot totals -> CSR offsets -> scatter into the result area
+        dp.slot_total = totals;
+        ds_hist_kernel<<<grid, DS_THREADS, 0, st>>>(dp);
+        ds_scan_kernel<<<n, 256, 0, st>>>(dp);
+        scan_offsets_kernel<<<1, 1024, 0, st>>>(totals, n, work.o_off());
+        dp.keys_out = work.o_keys();
+        dp.csr_off = work.o_off();
+        ds_scatter_kernel<<<grid, DS_THREADS, 0, st>>>(dp);
+        CK(cudaGetLastError());
+        ix->tm.kernel_launches += 4;
+    };
+    if (ix->pages.empty()) {
+        CK(cudaMemsetAsync(work.o_off(), 0, (static_cast<size_t>(n) + 1) * 8, st));
+    } else if (!two) {
+        dp.pass = 0;
+        final_pass(total1);
+    } else {
+        work.d_cand.ensure(static_cast<uint64_t>(n) * cap * 8);
+        dp.pass = 1;
+        dp.slot_total = total1;
+        dp.keys_out = work.d_cand.as<uint64_t>();
+        ds_hist_kernel<<<grid, DS_THREADS, 0, st>>>(dp);
+        ds_scan_kernel<<<n, 256, 0, st>>>(dp);
+        ds_scatter_kernel<<<grid, DS_THREADS, 0, st>>>(dp);
+        CK(cudaGetLastError());
+        ix->tm.kernel_launches += 3;
+        dp.pass = 2;
+        dp.keys_in = work.d_cand.as<uint64_t>();
+        dp.in_count = total1;
+        final_pass(total2);
+    }
+    CK(cudaMemcpyAsync(work.o_flags(), src.d_flags(), 8, cudaMemcpyDeviceToDevice, st));
+}
+
 // Synchronous exhaustive pass over the given queries of the batch in `src`, in workspace-bounded
-// sub-batches through the aux buffers: every real document of the shard can become a candidate
+// sub-batches through the aux buffers: every real document of the shard can become a result
 // (cap = shard_real_docs), so nothing is ever dropped.  Used for threshold <= 0 without a small
 // limit, for queries whose candidates overflowed the fused path, and for queries beyond 16 planes.
 void run_exhaustive(cobsgpu_index* ix, const Slot& src, const std::vector<uint32_t>& ids,
@@ -1170,54 +1249,73 @@ void run_exhaustive(cobsgpu_index* ix, const Slot& src, const std::vector<uint32
     if (ids.empty()) return;
     cudaStream_t st = ix->stream;
     Slot& work = ix->aux;
+    // queries beyond 16 bit-planes keep the u32 score vector + candidate keys + radix sort
+    std::vector<uint32_t> dense_ids, huge_ids;
+    for (uint32_t q : ids)
+        (src.koff[q + 1] - src.koff[q] > MAX_T_LONG ? huge_ids : dense_ids).push_back(q);
     PassPlan pl;
     pl.cap = std::max<uint32_t>(ix->shard_real_docs, 1);
     pl.limit = limit;
-    uint64_t per_q = static_cast<uint64_t>(pl.cap) * 8 * (pl.cap > FIN_SORT_MAX ? 2 : 1) +
-                     (limit ? std::min<uint64_t>(limit, pl.cap) : pl.cap) * 8;
-    const size_t sub = static_cast<size_t>(
-        std::max<uint64_t>(1, std::min<uint64_t>(ids.size(), ix->workspace_bytes / std::max<uint64_t>(per_q, 1))));
-    for (size_t b = 0; b < ids.size(); b += sub) {
-        const uint32_t n = static_cast<uint32_t>(std::min(sub, ids.size() - b));
-        const uint32_t* d_ql = upload_qlist(work, ids, b, n, st);
-        uint32_t max_T = 1;
-        for (size_t i = 0; i < n; ++i)
-            max_T = std::max(max_T, src.koff[ids[b + i] + 1] - src.koff[ids[b + i]]);
-        pl.lng = max_T > MAX_T_SHORT;
-        pl.mode = max_T > MAX_T_LONG ? MODE_DENSE32 : MODE_CAND;
-        work.d_out.ensure(out_bytes(work, n, pl));
-        work.d_res_count.ensure(static_cast<size_t>(n) * 4);
-        launch_pass_score(ix, src, work, d_ql, n, pl, work.o_cc(), st);
-        launch_select(ix, src, work, d_ql, n, pl, max_T, work.o_cc(), work.d_cand.as<uint64_t>(),
-                      work.d_res_count.as<uint32_t>(), pl.cap, false, st);
-        launch_csr(ix, src, work, n, pl.cap, st);
-        // header first (it tells how many keys there are), then the keys
-        work.h_out.ensure(work.out_keys);
-        {
-            PhaseScope ps(ix, PH_D2H, st);
-            CK(cudaMemcpyAsync(work.h_out.p, work.d_out.p, work.out_keys, cudaMemcpyDeviceToHost, st));
+    const uint64_t out_per_q = (limit ? std::min<uint64_t>(limit, pl.cap) : pl.cap) * 8;
+    for (int huge = 0; huge < 2; ++huge) {
+        const std::vector<uint32_t>& list = huge ? huge_ids : dense_ids;
+        if (list.empty()) continue;
+        uint64_t per_q;
+        if (huge) {
+            per_q = static_cast<uint64_t>(pl.cap) * 8 * (pl.cap > FIN_SORT_MAX ? 2 : 1) + out_per_q +
+                    ix->dense_pitch * 4;
+        } else {
+            const uint64_t n_chunks = div_ceil<uint64_t>(std::max<uint64_t>(ix->dense_pitch, pl.cap), DS_CHUNK);
+            per_q = ix->dense_pitch * 2 + n_chunks * 1024 + out_per_q + static_cast<uint64_t>(pl.cap) * 8;
         }
-        CK(cudaStreamSynchronize(st));
-        lists->emplace_back();
-        HostList& L = lists->back();
-        const uint64_t* off = reinterpret_cast<const uint64_t*>(work.h_out.as<char>() + work.out_off);
-        L.off.assign(off, off + n + 1);
-        const uint64_t total = L.off[n];
-        L.doc.resize(total);
-        L.score.resize(total);
-        if (total) {
-            work.h_out.ensure(work.out_keys + total * 8);
+        const size_t sub = static_cast<size_t>(
+            std::max<uint64_t>(1, std::min<uint64_t>(list.size(), ix->workspace_bytes / std::max<uint64_t>(per_q, 1))));
+        for (size_t b = 0; b < list.size(); b += sub) {
+            const uint32_t n = static_cast<uint32_t>(std::min(sub, list.size() - b));
+            const uint32_t* d_ql = upload_qlist(work, list, b, n, st);
+            uint32_t max_T = 1;
+            for (size_t i = 0; i < n; ++i)
+                max_T = std::max(max_T, src.koff[list[b + i] + 1] - src.koff[list[b + i]]);
+            pl.lng = max_T > MAX_T_SHORT;
+            pl.mode = MODE_DENSE32;
+            work.d_out.ensure(out_bytes(work, n, pl));
+            if (!huge) {
+                exhaustive_dense(ix, src, work, d_ql, n, max_T, limit, st);
+            } else {
+                work.d_res_count.ensure(static_cast<size_t>(n) * 4);
+                launch_pass_score(ix, src, work, d_ql, n, pl, work.o_cc(), st);
+                launch_select(ix, src, work, d_ql, n, pl, max_T, work.o_cc(), work.d_cand.as<uint64_t>(),
+                              work.d_res_count.as<uint32_t>(), pl.cap, false, st);
+                launch_csr(ix, src, work, n, pl.cap, st);
+            }
+            // header first (it tells how many keys there are), then the keys
+            work.h_out.ensure(work.out_keys);
             {
                 PhaseScope ps(ix, PH_D2H, st);
-                CK(cudaMemcpyAsync(work.h_out.as<char>() + work.out_keys, work.o_keys(), total * 8,
-                                   cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(work.h_out.p, work.d_out.p, work.out_keys, cudaMemcpyDeviceToHost, st));
             }
             CK(cudaStreamSynchronize(st));
-            decode_keys(reinterpret_cast<const uint64_t*>(work.h_out.as<char>() + work.out_keys), total,
-                        L.doc.data(), L.score.data());
+            lists->emplace_back();
+            HostList& L = lists->back();
+            const uint64_t* off = reinterpret_cast<const uint64_t*>(work.h_out.as<char>() + work.out_off);
+            L.off.assign(off, off + n + 1);
+            const uint64_t total = L.off[n];
+            L.doc.resize(total);
+            L.score.resize(total);
+            if (total) {
+                work.h_out.ensure(work.out_keys + total * 8);
+                {
+                    PhaseScope ps(ix, PH_D2H, st);
+                    CK(cudaMemcpyAsync(work.h_out.as<char>() + work.out_keys, work.o_keys(), total * 8,
+                                       cudaMemcpyDeviceToHost, st));
+                }
+                CK(cudaStreamSynchronize(st));
+                decode_keys(reinterpret_cast<const uint64_t*>(work.h_out.as<char>() + work.out_keys), total,
+                            L.doc.data(), L.score.data());
+            }
+            for (size_t i = 0; i < n; ++i)
+                (*where)[list[b + i]] = { static_cast<uint32_t>(lists->size() - 1), static_cast<uint32_t>(i) };
         }
-        for (size_t i = 0; i < n; ++i)
-            (*where)[ids[b + i]] = { static_cast<uint32_t>(lists->size() - 1), static_cast<uint32_t>(i) };
     }
 }
 

@@ -24,7 +24,8 @@
 //     per-bit extract+add could not keep up with HBM.
 //   * epilogue per item: CAND  -> bit-sliced compare against ceil(threshold*T), survivors are
 //                                 appended (warp-aggregated atomics) as sort keys;
-//                         DENSE8 -> the 128 counts are transposed out of the planes and stored;
+//                         DENSE8 / DENSE16 -> the 128 counts are transposed out of the planes and
+//                                   stored, one byte / one u16 per document (exhaustive lists);
 //                         DENSE32-> counts are added into a u32 score vector (flushed before the
 //                                   planes could overflow; any query length);
 //                         TOPK  -> every consumer warp keeps only the best `topk` of its 4096
@@ -40,8 +41,8 @@
 
 namespace cobsgpu {
 
-enum ScoreMode : int { MODE_CAND = 0, MODE_DENSE8 = 1, MODE_DENSE32 = 2, MODE_TOPK = 3 };
-static constexpr int SCORE_MODES = 4;
+enum ScoreMode : int { MODE_CAND = 0, MODE_DENSE8 = 1, MODE_DENSE32 = 2, MODE_TOPK = 3, MODE_DENSE16 = 4 };
+static constexpr int SCORE_MODES = 5;
 
 // one column tile of one page of the shard held by this device
 struct TileDesc {
@@ -72,6 +73,7 @@ struct ScoreParams {
     uint32_t topk;            // MODE_TOPK: results wanted per query (>= 1)
     // MODE_DENSE8 / MODE_DENSE32
     uint8_t* dense8;          // [nq_items * dense_pitch]
+    uint16_t* dense16;        // [nq_items * dense_pitch] (16 bit-planes, queries of <= 65 535 k-mers)
     uint32_t* dense32;        // [nq_items * dense_pitch] (zero-initialised)
     uint64_t dense_pitch;     // columns per slot, multiple of 128
     // dynamic work distribution: [0] next item, [1] CTAs finished (both zero between launches;
@@ -142,6 +144,7 @@ template <int H, int MODE, int NP>
 __global__ void __launch_bounds__(SCORE_MAX_THREADS, 3) score_kernel(const ScoreParams p) {
     static_assert(NP == SCORE_PLANES || NP == SCORE_PLANES_LONG, "8 or 16 bit-planes");
     static_assert(MODE != MODE_DENSE8 || NP == 8, "DENSE8 stores one byte per document");
+    static_assert(MODE != MODE_DENSE16 || NP == 16, "DENSE16 stores 16-bit counts");
     constexpr uint32_t MAXC = (1u << NP) - 1u;   // largest count the planes can hold
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t h = H > 0 ? static_cast<uint32_t>(H) : p.h;
@@ -311,6 +314,25 @@ __global__ void __launch_bounds__(SCORE_MAX_THREADS, 3) score_kernel(const Score
                     dst[2 * w] = lo;
                     dst[2 * w + 1] = hi;
                 }
+            } else if (MODE == MODE_DENSE16) {
+                uint4* dst = reinterpret_cast<uint4*>(p.dense16 + col);
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+#pragma unroll
+                    for (int gp = 0; gp < 4; ++gp) {
+                        // low and high count bytes of documents 8gp..8gp+7, interleaved to u16
+                        const uint32_t lo0 = planes_pack4(pl[w], 2 * gp);
+                        const uint32_t hi0 = planes_pack4<(NP > 8 ? 1 : 0)>(pl[w], 2 * gp);
+                        const uint32_t lo1 = planes_pack4(pl[w], 2 * gp + 1);
+                        const uint32_t hi1 = planes_pack4<(NP > 8 ? 1 : 0)>(pl[w], 2 * gp + 1);
+                        uint4 v;
+                        v.x = __byte_perm(lo0, hi0, 0x5140);
+                        v.y = __byte_perm(lo0, hi0, 0x7362);
+                        v.z = __byte_perm(lo1, hi1, 0x5140);
+                        v.w = __byte_perm(lo1, hi1, 0x7362);
+                        dst[4 * w + gp] = v;
+                    }
+                }
             } else {
                 uint4* dst = reinterpret_cast<uint4*>(p.dense32 + col);
 #pragma unroll
@@ -410,7 +432,7 @@ __global__ void __launch_bounds__(SCORE_MAX_THREADS, 3) score_kernel(const Score
             acc += 1;
         }
 
-        if (MODE == MODE_DENSE8 || MODE == MODE_DENSE32) {
+        if (MODE == MODE_DENSE8 || MODE == MODE_DENSE16 || MODE == MODE_DENSE32) {
             flush_dense();
         } else {
             // threshold in bit-sliced form, then append the survivors as sort keys

@@ -213,3 +213,26 @@ def test_handles_with_different_tile_widths_share_a_device():
                 assert as_list(r) == oracle.search(o, q, 0.05, 0)
     wide.close()
     narrow.close()
+
+
+@pytest.mark.parametrize("kind,n_docs,sig,h,ps", [
+    (KIND_CLASSIC, 70000, [53], 3, 0), (KIND_CLASSIC, 5000, [301], 1, 0),
+    (KIND_COMPACT, 40000, [61, 97, 31, 43, 59], 3, 1024), (KIND_COMPACT, 600, [331, 400, 123], 1, 32),
+])
+def test_exhaustive_lists_counting_sort(kind, n_docs, sig, h, ps):
+    """threshold 0 / all results (Search::search's defaults, benchmark-fpr): every document comes
+    back, ordered by a stable counting sort on the device; one-byte and two-byte counts, limits
+    beyond the top-k epilogue, thresholds that overflow the candidate slots"""
+    g, o = pair(kind, n_docs, sig, h, page_size=ps, seed=n_docs + 9)
+    qs = [rq(n_docs + i, L) for i, L in enumerate([100, 285, 286, 1030, 45, 5000])]
+    if h == 1:
+        qs = qs[:]          # (no single-hash query in this list)
+    for thr, k in ((0.0, 0), (0.0, 3000), (0.02, 0), (0.0, 1025), (0.2, 0)):
+        got = g.search_batch(qs, thr, k)
+        for q, r in zip(qs, got):
+            assert as_list(r) == oracle.search(o, q, thr, k), (thr, k, len(q))
+    # tiny workspace: many sub-batches
+    g.set_option("workspace_mb", 1)
+    for q, r in zip(qs, g.search_batch(qs, 0.0, 0)):
+        assert as_list(r) == oracle.search(o, q, 0.0, 0)
+    g.close()
