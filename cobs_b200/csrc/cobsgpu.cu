@@ -137,6 +137,67 @@ struct PinBuf {
     }
 };
 
+// Result arrays (documents / scores) can run to hundreds of megabytes per call when a query
+// returns every document: a grow-only buffer that never value-initialises (std::vector::resize
+// would zero-fill what the decode overwrites a moment later) with the few vector operations the
+// result assembly uses.
+struct U32Buf {
+    uint32_t* p = nullptr;
+    size_t n = 0, cap = 0;
+    U32Buf() = default;
+    U32Buf(const U32Buf&) = delete;
+    U32Buf(U32Buf&& o) noexcept : p(o.p), n(o.n), cap(o.cap) {
+        o.p = nullptr;
+        o.n = o.cap = 0;
+    }
+    U32Buf& operator=(const U32Buf& o) {
+        if (this != &o) {
+            resize(o.n);
+            if (o.n) std::memcpy(p, o.p, o.n * 4);
+        }
+        return *this;
+    }
+    ~U32Buf() { std::free(p); }
+    void reserve(size_t m) {
+        if (m <= cap) return;
+        m = std::max(m, cap + cap / 2);
+        void* q = std::realloc(p, m * 4);
+        if (!q) throw std::bad_alloc();
+        p = static_cast<uint32_t*>(q);
+        cap = m;
+    }
+    void resize(size_t m) {   // new elements are NOT initialised
+        reserve(m);
+        n = m;
+    }
+    void clear() { n = 0; }
+    size_t size() const { return n; }
+    uint32_t* data() { return p; }
+    const uint32_t* data() const { return p; }
+    uint32_t* begin() { return p; }
+    uint32_t* end() { return p + n; }
+    const uint32_t* begin() const { return p; }
+    const uint32_t* end() const { return p + n; }
+    uint32_t& operator[](size_t i) { return p[i]; }
+    const uint32_t& operator[](size_t i) const { return p[i]; }
+    void push_back(uint32_t v) {
+        reserve(n + 1);
+        p[n++] = v;
+    }
+    // append [first, last); `where` must be end()
+    void insert(const uint32_t*, const uint32_t* first, const uint32_t* last) {
+        const size_t m = static_cast<size_t>(last - first);
+        reserve(n + m);
+        if (m) std::memcpy(p + n, first, m * 4);
+        n += m;
+    }
+    void swap(U32Buf& o) {
+        std::swap(p, o.p);
+        std::swap(n, o.n);
+        std::swap(cap, o.cap);
+    }
+};
+
 struct LocalPage {
     uint32_t global_page;
     uint64_t sig;
@@ -186,7 +247,7 @@ struct Slot {
     std::vector<uint32_t> huge_ids;      // queries of more than 65 535 k-mers
     // collected result (valid until the slot is submitted again)
     std::vector<uint64_t> r_off;
-    std::vector<uint32_t> r_doc, r_score;
+    U32Buf r_doc, r_score;
 
     int* d_flags() const { return d_meta.as<int>(); }
     uint32_t* d_bad() const { return reinterpret_cast<uint32_t*>(d_meta.as<char>() + meta_bad); }
@@ -309,7 +370,7 @@ struct cobsgpu_index {
 
     // results of the last cobsgpu_search_batch call
     std::vector<uint64_t> r_off;
-    std::vector<uint32_t> r_doc, r_score;
+    U32Buf r_doc, r_score;
 
     // timers
     cobsgpu_timers tm{};
@@ -507,8 +568,11 @@ void build_tiles(cobsgpu_index* ix) {
     ix->tiles.clear();
     for (auto& lp : ix->pages) {
         const uint32_t n = div_ceil<uint32_t>(lp.rb16, W);
-        // even split; 128-byte aligned tile width when that still fits in W
-        uint32_t tb = round_up<uint32_t>(div_ceil<uint32_t>(lp.rb16, n), 128);
+        // Even split: an item costs about the same whatever its width (its k-mers are fetched
+        // one row slice at a time), so a ragged last tile wastes its share of the time -- a
+        // 15.6 KB shard row cut into 7 x 2048 + 1296 bytes ran 4.5 % below 8 x ~1950.  Widths are
+        // multiples of 64 bytes (whole DRAM sectors) when that still fits in W, else of 16.
+        uint32_t tb = round_up<uint32_t>(div_ceil<uint32_t>(lp.rb16, n), 64);
         if (tb > W) tb = round_up<uint32_t>(div_ceil<uint32_t>(lp.rb16, n), 16);
         for (uint32_t off = 0; off < lp.rb16; off += tb) {
             TileDesc t{};
@@ -1141,14 +1205,27 @@ size_t out_bytes(Slot& work, uint32_t n_slots, const PassPlan& pl) {
 
 struct HostList {
     std::vector<uint64_t> off;   // [n_slots + 1]
-    std::vector<uint32_t> doc, score;
+    U32Buf doc, score;
 };
 
 void decode_keys(const uint64_t* keys, uint64_t n, uint32_t* doc, uint32_t* score) {
-    for (uint64_t i = 0; i < n; ++i) {
-        doc[i] = key_doc(keys[i]);
-        score[i] = key_score(keys[i]);
+    auto part = [=](uint64_t a, uint64_t b) {
+        for (uint64_t i = a; i < b; ++i) {
+            doc[i] = key_doc(keys[i]);
+            score[i] = key_score(keys[i]);
+        }
+    };
+    // exhaustive lists of large indices are memory-bound on the host: split them over threads
+    const uint64_t per_thread = 1ull << 20;
+    unsigned hw = std::thread::hardware_concurrency();
+    const uint64_t nt = std::min<uint64_t>(std::max(1u, std::min(hw, 8u)), n / per_thread);
+    if (nt <= 1) {
+        part(0, n);
+        return;
     }
+    std::vector<std::thread> th;
+    for (uint64_t t = 0; t < nt; ++t) th.emplace_back(part, n * t / nt, n * (t + 1) / nt);
+    for (auto& t : th) t.join();
 }
 
 void throw_bad_base(uint32_t query) {
@@ -1598,12 +1675,12 @@ struct cobsgpu_group {
         DevBuf d_mkeys, d_mcount;    // merged lists on the leader
         DevBuf d_stage_keys, d_stage_counts;   // copies of peers' blocks when peer access is missing
         std::vector<uint64_t> r_off;
-        std::vector<uint32_t> r_doc, r_score;
+        U32Buf r_doc, r_score;
     } gs[cobsgpu_index::N_SLOTS];
     int next = 0;
     // result of the last cobsgpu_group_search_batch call
     std::vector<uint64_t> r_off;
-    std::vector<uint32_t> r_doc, r_score;
+    U32Buf r_doc, r_score;
     // a copy of the caller's queries that stays valid while batches are in flight is not
     // needed: cudaMemcpyAsync from pageable memory is staged before it returns
 

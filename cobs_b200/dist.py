@@ -74,23 +74,29 @@ class ShardedSearch:
         key = (nq, k, str(dev), parity)
         b = self._bufs.get(key)
         if b is None:
-            h = (nq + 1) // 2                      # int64 words holding the int32 counts
-            L = h + nq * self.rpq
-            block = torch.zeros(L, dtype=torch.int64, device=dev)
-            gathered = torch.zeros(self.world * L, dtype=torch.int64, device=dev)
-            g2 = gathered.view(self.world, L)
-            b = {
-                "block": block,
-                "counts": block[:h].view(torch.int32)[:nq],
-                "keys": block[h:].view(nq, self.rpq),
-                "gathered": gathered,
-                "all_counts": g2[:, :h].view(torch.int32)[:, :nq],
-                "all_keys": g2[:, h:].view(self.world, nq, self.rpq),
-                "out_counts": torch.zeros(nq, dtype=torch.int32, device=dev),
-                "out_keys": torch.zeros((nq, k), dtype=torch.int64, device=dev),
-            }
-            self._bufs[key] = b
+            # every buffer set of the ring at once: an allocation stalls the device, and a set
+            # that is first needed in the middle of a stream of batches would stall it there
+            for par in range(self.depth):
+                self._bufs[(nq, k, str(dev), par)] = self._make_buffers(nq, k, dev)
+            b = self._bufs[key]
         return b
+
+    def _make_buffers(self, nq, k, dev):
+        h = (nq + 1) // 2                      # int64 words holding the int32 counts
+        L = h + nq * self.rpq
+        block = torch.zeros(L, dtype=torch.int64, device=dev)
+        gathered = torch.zeros(self.world * L, dtype=torch.int64, device=dev)
+        g2 = gathered.view(self.world, L)
+        return {
+            "block": block,
+            "counts": block[:h].view(torch.int32)[:nq],
+            "keys": block[h:].view(nq, self.rpq),
+            "gathered": gathered,
+            "all_counts": g2[:, :h].view(torch.int32)[:, :nq],
+            "all_keys": g2[:, h:].view(self.world, nq, self.rpq),
+            "out_counts": torch.zeros(nq, dtype=torch.int32, device=dev),
+            "out_keys": torch.zeros((nq, k), dtype=torch.int64, device=dev),
+        }
 
     def search_device(self, d_queries, off, threshold, num_results):
         """d_queries: uint8 tensor on this rank's device holding the packed batch; off: host
