@@ -12,7 +12,7 @@ section 8d realisation):
   cfg4  classic, 1 000 000 docs, 1 048 573 rows (131 GB), h=3, 16 384 queries per step: the
         north-star configuration and the HEADLINE of every run (document-axis shards for N > 1)
   cfg2  classic, 100 000 docs, 8 388 593 signature rows (104.9 GB in HBM), h=3, 10 000 queries
-  cfg3  compact, 1 000 000 docs, 8 pages of 16 384 B, h=4, 512 queries per step
+  cfg3  compact, 1 000 000 docs, 8 pages of 16 384 B, h=4, 2 048 queries per step
   cfg5  compact, 10 000 000 docs, 77 pages of 16 384 B (~600 GB): needs the HBM of >= 4 GPUs
 One invocation times the headline workload and -- in `secondary` -- cfg2 (every N; for N > 1 with
 the shard policy chosen from the index size), cfg3 (N = 1) and cfg5 (N = 8).
@@ -56,15 +56,15 @@ WORKLOADS = {
     "cfg4": dict(kind=0, n_docs=1_000_000, sig=[1_048_573], page_size=0, h=3, nq=16_384, thr_hits=0.11,
                  desc="classic index, 1000000 docs, 1048573 rows (131 GB HBM), h=3, k=31, "
                       "16384 random 100-bp queries/step"),
-    "cfg3": dict(kind=1, n_docs=1_000_000, page_size=16_384, h=4, nq=512, thr_hits=0.07,
+    "cfg3": dict(kind=1, n_docs=1_000_000, page_size=16_384, h=4, nq=2_048, thr_hits=0.07,
                  sig=[int(196_613 * 1.5 ** p) for p in range(8)],
                  desc="compact index, 1000000 docs, 8 pages x 16384 B (158.7 GB HBM), h=4, k=31, "
-                      "512 random 100-bp queries/step"),
+                      "2048 random 100-bp queries/step"),
     # BASELINE.json configs[4]: index larger than one GPU's HBM -> needs >= 4 GPUs
-    "cfg5": dict(kind=1, n_docs=10_000_000, page_size=16_384, h=4, nq=256, thr_hits=0.07,
+    "cfg5": dict(kind=1, n_docs=10_000_000, page_size=16_384, h=4, nq=1_024, thr_hits=0.07,
                  sig=[int(100_003 * 1.0345 ** p) for p in range(77)],
                  desc="compact index, 10000000 docs, 77 pages x 16384 B (~600 GB, document-sharded), "
-                      "h=4, k=31, 256 random 100-bp queries/step"),
+                      "h=4, k=31, 1024 random 100-bp queries/step"),
     # small variant for functional checks on any GPU
     "tiny": dict(kind=0, n_docs=100_000, sig=[65_521], page_size=0, h=3, nq=2_000, thr_hits=0.1,
                  desc="classic index, 100000 docs, 65521 rows (0.8 GB), h=3, k=31"),
@@ -702,8 +702,10 @@ def run_patterns(env, cfg, sig, index, search, lo, hi, d_batches, off, warmup, s
         n_fpr = 16
         blob, off_f = make_batch(7100, n_fpr, 1030)
         pin = torch.from_numpy(blob).pin_memory().numpy()
-        index.search_packed(pin[:1030 * 2], off_f[:3], 0.0, 0, raw=True)
+        index.search_packed(pin, off_f, 0.0, 0, raw=True)      # warm-up: buffers reach their size
         torch.cuda.synchronize()
+        blob, off_f = make_batch(7101, n_fpr, 1030)
+        pin = torch.from_numpy(blob).pin_memory().numpy()
         t0 = time.perf_counter()
         roff, doc, score = index.search_packed(pin, off_f, 0.0, 0, raw=True)
         dt = time.perf_counter() - t0
@@ -729,6 +731,18 @@ def run_patterns(env, cfg, sig, index, search, lo, hi, d_batches, off, warmup, s
             ts = np.array(ts[20:]) * 1e6
             lat[name] = {"p50_us": float(np.percentile(ts, 50)), "p90_us": float(np.percentile(ts, 90)),
                          "p99_us": float(np.percentile(ts, 99))}
+        # a single LONG query (a gene against the index): k-split score kernel + counting sort
+        for name, qlen in (("kmers1000_threshold0.8", 1030), ("kmers10000_threshold0.8", 10_030)):
+            blob_l, off_l = make_batch(7300, 24, qlen)
+            pin_l = torch.from_numpy(blob_l).pin_memory().numpy()
+            ts = []
+            for i in range(24):
+                q = pin_l[i * qlen:(i + 1) * qlen]
+                t0 = time.perf_counter()
+                index.search_packed(q, off_l[:2], THRESHOLD, 0, raw=True)
+                ts.append(time.perf_counter() - t0)
+            ts = np.array(ts[4:]) * 1e6
+            lat[name] = {"p50_us": float(np.percentile(ts, 50)), "p90_us": float(np.percentile(ts, 90))}
         lat["kernel_floor_us"] = ("one CTA streams %d row slices per tile; a lone CTA is "
                                   "latency-bound" % (T_KMERS * cfg["h"]))
         out["single_query_latency"] = lat

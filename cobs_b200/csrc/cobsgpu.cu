@@ -241,6 +241,7 @@ struct Slot {
     uint64_t limit = 0;
     int mode = 0;                        // MODE_CAND / MODE_TOPK, or -1: exhaustive at collect
     bool lng = false;
+    bool ksplit = false;                 // few long queries: k-split score kernel at collect
     uint32_t cap = 0;
     uint64_t spec_keys = 0;              // keys copied back speculatively with the header
     std::vector<uint32_t> main_ids;      // queries of the main pass when not all of them
@@ -848,6 +849,7 @@ ScoreFn pick_score(uint32_t h, int mode, bool lng) {
     case MODE_TOPK: return lng ? pick_h<MODE_TOPK, 16>(h) : pick_h<MODE_TOPK, 8>(h);
     case MODE_DENSE8: return pick_h<MODE_DENSE8, 8>(h);
     case MODE_DENSE16: return pick_h<MODE_DENSE16, 16>(h);
+    case MODE_KSPLIT: return pick_h<MODE_KSPLIT, 8>(h);
     default: return pick_h<MODE_DENSE32, 8>(h);
     }
 }
@@ -857,7 +859,7 @@ void launch_score(cobsgpu_index* ix, ScoreParams sp, int mode, bool lng, cudaStr
     const uint32_t h = ix->num_hashes;
     ScoreFn fn = pick_score(h, mode, lng);
     const int threads = static_cast<int>((ix->ncw + 1) * 32);
-    if (mode == MODE_DENSE8 || mode == MODE_DENSE32) lng = false;
+    if (mode == MODE_DENSE8 || mode == MODE_DENSE32 || mode == MODE_KSPLIT) lng = false;
     if (mode == MODE_DENSE16) lng = true;
     cobsgpu_index::ScoreCfg& cfg = ix->score_cfg[mode][lng ? 1 : 0];
     if (!cfg.valid) {
@@ -896,7 +898,8 @@ void launch_score(cobsgpu_index* ix, ScoreParams sp, int mode, bool lng, cudaStr
     // running concurrently on different streams never share a pair (the last CTA of a launch
     // re-arms its own pair)
     sp.work = ix->d_work + 2 * (ix->work_slot++ % cobsgpu_index::WORK_RING);
-    const uint64_t items = static_cast<uint64_t>(sp.nq_items) * sp.n_tiles;
+    if (mode != MODE_KSPLIT) sp.n_kchunks = 1;
+    const uint64_t items = static_cast<uint64_t>(sp.nq_items) * sp.n_tiles * sp.n_kchunks;
     const uint32_t grid = static_cast<uint32_t>(
         std::min<uint64_t>(items, static_cast<uint64_t>(cfg.occupancy) * ix->sm_count));
     PhaseScope ps(ix, PH_SCORE, st);
@@ -1054,6 +1057,8 @@ ScoreParams base_params(cobsgpu_index* ix, const Slot& src, const uint32_t* d_ql
     sp.nq_items = n_slots;
     sp.thr = src.d_thr();
     sp.dense_pitch = ix->dense_pitch;
+    sp.kchunk = 0;
+    sp.n_kchunks = 1;
     return sp;
 }
 
@@ -1086,7 +1091,7 @@ struct PassPlan {
 void launch_select(cobsgpu_index* ix, const Slot& src, Slot& work, const uint32_t* d_qlist,
                    uint32_t n_slots, const PassPlan& pl, uint32_t max_T, uint32_t* cand_count,
                    uint64_t* out_keys, uint32_t* out_counts, uint32_t stride, bool report_bad,
-                   cudaStream_t st) {
+                   cudaStream_t st, bool fuse_csr = false) {
     PhaseScope ps(ix, PH_SELECT, st);
     const uint32_t cap = pl.cap;
     uint64_t* cand = work.d_cand.as<uint64_t>();
@@ -1127,6 +1132,12 @@ void launch_select(cobsgpu_index* ix, const Slot& src, Slot& work, const uint32_
     fp.stride = stride;
     fp.fin_sort_max = std::min<uint32_t>(FIN_SORT_MAX, pow2_ceil(std::max<uint32_t>(cap, 32)));
     fp.large_in_scratch = large_in_scratch ? 1 : 0;
+    if (fuse_csr) {   // small batch: offsets + keys + flags written by the same (single) CTA
+        fp.csr_off = work.o_off();
+        fp.csr_keys = work.o_keys();
+        fp.flags_src = src.d_flags();
+        fp.flags_dst = work.o_flags();
+    }
     const size_t smem = static_cast<size_t>(fp.fin_sort_max) * 8;
     static bool attr_set[64] = {};
     if (!attr_set[ix->device & 63]) {
@@ -1245,8 +1256,19 @@ const uint32_t* upload_qlist(Slot& work, const std::vector<uint32_t>& ids, size_
 // per document (DENSE8 / DENSE16), then a stable multi-CTA counting sort on the score
 // (densesort.cuh) writes the ordered keys straight into the CSR area of work.d_out.
 void exhaustive_dense(cobsgpu_index* ix, const Slot& src, Slot& work, const uint32_t* d_ql,
-                      uint32_t n, uint32_t max_T, uint64_t limit, cudaStream_t st) {
-    const bool two = max_T > MAX_T_SHORT;
+                      uint32_t n, uint32_t max_T, uint64_t limit, bool ksplit, cudaStream_t st) {
+    // k-split: the k-mers of every query are cut into chunks that become work items of their own
+    // (partial counts added into the u16 vector), sized so that the items fill the GPU
+    uint32_t kchunk = 0, n_kchunks = 1;
+    if (ksplit) {
+        const uint64_t per_chunk = std::max<uint64_t>(1, static_cast<uint64_t>(n) * ix->tiles.size());
+        const uint64_t want = div_ceil<uint64_t>(2ull * 3 * ix->sm_count, per_chunk);   // ~2 waves of CTAs
+        kchunk = round_up<uint32_t>(std::max<uint32_t>(8, static_cast<uint32_t>(div_ceil<uint64_t>(max_T, want))), 8);
+        kchunk = std::min<uint32_t>(kchunk, 248);
+        n_kchunks = div_ceil<uint32_t>(max_T, kchunk);
+        if (n_kchunks <= 1) ksplit = false;
+    }
+    const bool two = ksplit || max_T > MAX_T_SHORT;
     const uint32_t cap = std::max<uint32_t>(ix->shard_real_docs, 1);
     const size_t esz = two ? 2 : 1;
     const uint32_t dense_cols = static_cast<uint32_t>(ix->dense_pitch);
@@ -1261,7 +1283,9 @@ void exhaustive_dense(cobsgpu_index* ix, const Slot& src, Slot& work, const uint
     ScoreParams sp = base_params(ix, src, d_ql, n);
     sp.dense8 = work.d_dense.as<uint8_t>();
     sp.dense16 = work.d_dense.as<uint16_t>();
-    launch_score(ix, sp, two ? MODE_DENSE16 : MODE_DENSE8, two, st);
+    sp.kchunk = kchunk;
+    sp.n_kchunks = n_kchunks;
+    launch_score(ix, sp, ksplit ? MODE_KSPLIT : (two ? MODE_DENSE16 : MODE_DENSE8), two, st);
 
     PhaseScope ps(ix, PH_SELECT, st);
     const uint32_t np = static_cast<uint32_t>(ix->pages.size());
@@ -1322,7 +1346,7 @@ void exhaustive_dense(cobsgpu_index* ix, const Slot& src, Slot& work, const uint
 // limit, for queries whose candidates overflowed the fused path, and for queries beyond 16 planes.
 void run_exhaustive(cobsgpu_index* ix, const Slot& src, const std::vector<uint32_t>& ids,
                     uint64_t limit, std::vector<HostList>* lists,
-                    std::vector<std::pair<uint32_t, uint32_t>>* where) {
+                    std::vector<std::pair<uint32_t, uint32_t>>* where, bool ksplit = false) {
     if (ids.empty()) return;
     cudaStream_t st = ix->stream;
     Slot& work = ix->aux;
@@ -1357,7 +1381,7 @@ void run_exhaustive(cobsgpu_index* ix, const Slot& src, const std::vector<uint32
             pl.mode = MODE_DENSE32;
             work.d_out.ensure(out_bytes(work, n, pl));
             if (!huge) {
-                exhaustive_dense(ix, src, work, d_ql, n, max_T, limit, st);
+                exhaustive_dense(ix, src, work, d_ql, n, max_T, limit, ksplit, st);
             } else {
                 work.d_res_count.ensure(static_cast<size_t>(n) * 4);
                 launch_pass_score(ix, src, work, d_ql, n, pl, work.o_cc(), st);
@@ -1458,9 +1482,14 @@ Slot& submit_batch(cobsgpu_index* ix, const char* queries, const uint64_t* offse
                    uint32_t q1, double threshold, uint64_t limit) {
     Slot& sl = take_slot(ix);
     WarmRing warm{ ix, sl, sl.footprint() };
-    prepare_batch(ix, sl, queries, false, offsets, q0, q1, threshold, ix->s_in);
-    CK(cudaEventRecord(sl.ev(sl.ev_in), ix->s_in));
     const uint32_t nq = q1 - q0;
+    // A handful of queries (the `cobs query <string>` pattern) is latency-bound: everything runs
+    // on ONE stream -- no cross-stream hand-offs -- and K3 formats the result in its own launch.
+    const bool small = nq <= FIN_WARPS;
+    cudaStream_t st_in = small ? ix->stream : ix->s_in;
+    cudaStream_t st_out = small ? ix->stream : ix->s_out;
+    prepare_batch(ix, sl, queries, false, offsets, q0, q1, threshold, st_in);
+    if (!small) CK(cudaEventRecord(sl.ev(sl.ev_in), st_in));
     sl.q0 = q0;
     sl.threshold = threshold;
     sl.limit = limit;
@@ -1484,8 +1513,13 @@ Slot& submit_batch(cobsgpu_index* ix, const char* queries, const uint64_t* offse
     sl.busy = true;
     sl.ticket = ++ix->ticket_counter;
     cudaStream_t st = ix->stream;
-    CK(cudaStreamWaitEvent(st, sl.ev_in, 0));
-    if (n_main == 0 || !plan_main_pass(ix, sl, threshold, limit, main_max_T, &pl)) {
+    if (!small) CK(cudaStreamWaitEvent(st, sl.ev_in, 0));
+    // A few LONG queries (a gene or a plasmid against the index): with one work item per (query,
+    // tile) only n_tiles CTAs would run, each walking a latency chain of thousands of k-mers.
+    // Such batches take the k-split score kernel + the dense counting sort at collect instead.
+    sl.ksplit = sl.huge_ids.empty() && main_max_T >= 256 &&
+                static_cast<uint64_t>(n_main) * ix->tiles.size() < 2ull * 3 * ix->sm_count;
+    if (n_main == 0 || sl.ksplit || !plan_main_pass(ix, sl, threshold, limit, main_max_T, &pl)) {
         // exhaustive at collect; only the invalid-base flag is needed from the device
         sl.layout_out(0);
         sl.d_out.ensure(sl.out_keys);
@@ -1502,23 +1536,24 @@ Slot& submit_batch(cobsgpu_index* ix, const char* queries, const uint64_t* offse
     sl.d_out.ensure(ob);
     sl.d_res_count.ensure(static_cast<size_t>(n_main) * 4);
     launch_pass_score(ix, sl, sl, d_ql, n_main, pl, sl.o_cc(), st);
+    const bool fuse_csr = small && sl.huge_ids.empty();
     launch_select(ix, sl, sl, d_ql, n_main, pl, main_max_T, sl.o_cc(), sl.d_cand.as<uint64_t>(),
-                  sl.d_res_count.as<uint32_t>(), pl.cap, false, st);
-    launch_csr(ix, sl, sl, n_main, pl.cap, st);
-    CK(cudaEventRecord(sl.ev(sl.ev_main), st));
+                  sl.d_res_count.as<uint32_t>(), pl.cap, false, st, fuse_csr);
+    if (!fuse_csr) launch_csr(ix, sl, sl, n_main, pl.cap, st);
+    if (!small) CK(cudaEventRecord(sl.ev(sl.ev_main), st));
     // ONE device-to-host copy in the common case: the header and the first spec_keys keys
     const uint64_t max_keys = (ob - sl.out_keys) / 8;
     // (sized from what the previous batch returned, with headroom)
     sl.spec_keys = std::min<uint64_t>(
         max_keys, std::max<uint64_t>(std::max<uint64_t>(8192, 8ull * n_main), ix->spec_hint + ix->spec_hint / 4));
     sl.h_out.ensure(sl.out_keys + sl.spec_keys * 8);
-    CK(cudaStreamWaitEvent(ix->s_out, sl.ev_main, 0));
+    if (!small) CK(cudaStreamWaitEvent(st_out, sl.ev_main, 0));
     {
-        PhaseScope ps(ix, PH_D2H, ix->s_out);
+        PhaseScope ps(ix, PH_D2H, st_out);
         CK(cudaMemcpyAsync(sl.h_out.p, sl.d_out.p, sl.out_keys + sl.spec_keys * 8, cudaMemcpyDeviceToHost,
-                           ix->s_out));
+                           st_out));
     }
-    CK(cudaEventRecord(sl.ev(sl.ev_out), ix->s_out));
+    CK(cudaEventRecord(sl.ev(sl.ev_out), st_out));
     return sl;
 }
 
@@ -1588,7 +1623,7 @@ void collect_batch(cobsgpu_index* ix, Slot& sl) {
             return;
         }
     }
-    run_exhaustive(ix, sl, redo, sl.limit, &lists, &where);
+    run_exhaustive(ix, sl, redo, sl.limit, &lists, &where, sl.ksplit);
     uint64_t run = 0;
     for (uint32_t i = 0; i < nq; ++i) {
         const HostList& L = lists[where[i].first];

@@ -34,6 +34,11 @@
 //                                  prefix-limited tie mask.  The union of the per-warp lists
 //                                  contains the query's global top-k, never overflows, and is
 //                                  tiny, so `-t 0 -l k` no longer materialises every document.
+//                         KSPLIT -> a work item is (query, tile, CHUNK of the query's k-mers): the
+//                                  partial counts of the chunk are added into a u16 score vector
+//                                  with packed atomics.  For a few long queries (one gene against
+//                                  the index) the chunks spread one query over every SM instead of
+//                                  leaving it to n_tiles CTAs whose k-mers form a latency chain.
 //   * NP = number of bit-planes per word: 8 (queries of <= 255 k-mers) or 16 (<= 65 535).
 #pragma once
 
@@ -41,8 +46,9 @@
 
 namespace cobsgpu {
 
-enum ScoreMode : int { MODE_CAND = 0, MODE_DENSE8 = 1, MODE_DENSE32 = 2, MODE_TOPK = 3, MODE_DENSE16 = 4 };
-static constexpr int SCORE_MODES = 5;
+enum ScoreMode : int { MODE_CAND = 0, MODE_DENSE8 = 1, MODE_DENSE32 = 2, MODE_TOPK = 3, MODE_DENSE16 = 4,
+                       MODE_KSPLIT = 5 };
+static constexpr int SCORE_MODES = 6;
 
 // one column tile of one page of the shard held by this device
 struct TileDesc {
@@ -76,6 +82,8 @@ struct ScoreParams {
     uint16_t* dense16;        // [nq_items * dense_pitch] (16 bit-planes, queries of <= 65 535 k-mers)
     uint32_t* dense32;        // [nq_items * dense_pitch] (zero-initialised)
     uint64_t dense_pitch;     // columns per slot, multiple of 128
+    // MODE_KSPLIT: k-mers per chunk (multiple of 8, <= 248) and chunks per query; 1 chunk otherwise
+    uint32_t kchunk, n_kchunks;
     // dynamic work distribution: [0] next item, [1] CTAs finished (both zero between launches;
     // the last CTA to finish resets them)
     unsigned long long* work;
@@ -145,6 +153,7 @@ __global__ void __launch_bounds__(SCORE_MAX_THREADS, 3) score_kernel(const Score
     static_assert(NP == SCORE_PLANES || NP == SCORE_PLANES_LONG, "8 or 16 bit-planes");
     static_assert(MODE != MODE_DENSE8 || NP == 8, "DENSE8 stores one byte per document");
     static_assert(MODE != MODE_DENSE16 || NP == 16, "DENSE16 stores 16-bit counts");
+    static_assert(MODE != MODE_KSPLIT || NP == 8, "a chunk holds at most 248 k-mers");
     constexpr uint32_t MAXC = (1u << NP) - 1u;   // largest count the planes can hold
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t h = H > 0 ? static_cast<uint32_t>(H) : p.h;
@@ -173,7 +182,7 @@ __global__ void __launch_bounds__(SCORE_MAX_THREADS, 3) score_kernel(const Score
     }
     __syncthreads();
 
-    const uint64_t n_items = static_cast<uint64_t>(p.nq_items) * p.n_tiles;
+    const uint64_t n_items = static_cast<uint64_t>(p.nq_items) * p.n_tiles * (MODE == MODE_KSPLIT ? p.n_kchunks : 1u);
     uint32_t s = 0, par = 0;   // ring position / phase parity, advanced identically by both roles
     uint32_t iq = 0, iq_par = 0;   // item-queue position / parity, likewise
 
@@ -199,11 +208,22 @@ __global__ void __launch_bounds__(SCORE_MAX_THREADS, 3) score_kernel(const Score
                 iq_par ^= 1;
             }
             if (item >= n_items) break;
-            const uint32_t qi = static_cast<uint32_t>(item / p.n_tiles);
-            const uint32_t tile = static_cast<uint32_t>(item - static_cast<uint64_t>(qi) * p.n_tiles);
+            uint64_t qt = item;
+            uint32_t kc = 0;
+            if (MODE == MODE_KSPLIT) {
+                qt = item / p.n_kchunks;
+                kc = static_cast<uint32_t>(item - qt * p.n_kchunks);
+            }
+            const uint32_t qi = static_cast<uint32_t>(qt / p.n_tiles);
+            const uint32_t tile = static_cast<uint32_t>(qt - static_cast<uint64_t>(qi) * p.n_tiles);
             const uint32_t q = p.qlist ? p.qlist[qi] : qi;
             const TileDesc td = p.tiles[tile];
-            const uint32_t k0 = p.koff[q], T = p.koff[q + 1] - k0;
+            uint32_t k0 = p.koff[q], T = p.koff[q + 1] - k0;
+            if (MODE == MODE_KSPLIT) {   // this item's chunk of the query's k-mers
+                const uint32_t kb = kc * p.kchunk;
+                T = kb < T ? (T - kb < p.kchunk ? T - kb : p.kchunk) : 0;
+                k0 += kb;
+            }
             const uint64_t* hq = p.hashes + static_cast<uint64_t>(k0) * h;
             for (uint32_t t0 = 0; t0 < T; t0 += kpr) {
                 const uint32_t t = t0 + my_k;
@@ -252,11 +272,21 @@ __global__ void __launch_bounds__(SCORE_MAX_THREADS, 3) score_kernel(const Score
             iq_par ^= 1;
         }
         if (item >= n_items) break;
-        const uint32_t qi = static_cast<uint32_t>(item / p.n_tiles);
-        const uint32_t tile = static_cast<uint32_t>(item - static_cast<uint64_t>(qi) * p.n_tiles);
+        uint64_t qt = item;
+        uint32_t kc = 0;
+        if (MODE == MODE_KSPLIT) {
+            qt = item / p.n_kchunks;
+            kc = static_cast<uint32_t>(item - qt * p.n_kchunks);
+        }
+        const uint32_t qi = static_cast<uint32_t>(qt / p.n_tiles);
+        const uint32_t tile = static_cast<uint32_t>(qt - static_cast<uint64_t>(qi) * p.n_tiles);
         const uint32_t q = p.qlist ? p.qlist[qi] : qi;
         const TileDesc td = p.tiles[tile];
-        const uint32_t T = p.koff[q + 1] - p.koff[q];
+        uint32_t T = p.koff[q + 1] - p.koff[q];
+        if (MODE == MODE_KSPLIT) {
+            const uint32_t kb = kc * p.kchunk;
+            T = kb < T ? (T - kb < p.kchunk ? T - kb : p.kchunk) : 0;
+        }
         const bool active = threadIdx.x * 16 < td.bytes;
 
         uint32_t pl[4][NP];
@@ -432,7 +462,28 @@ __global__ void __launch_bounds__(SCORE_MAX_THREADS, 3) score_kernel(const Score
             acc += 1;
         }
 
-        if (MODE == MODE_DENSE8 || MODE == MODE_DENSE16 || MODE == MODE_DENSE32) {
+        if (MODE == MODE_KSPLIT) {
+            // partial counts of this chunk (<= 248) -> packed u16 adds, two documents per atomic;
+            // the sums stay below 65 536, so no carry crosses the halves
+            if (active && T != 0) {
+                uint32_t* dst = reinterpret_cast<uint32_t*>(
+                    p.dense16 + static_cast<uint64_t>(qi) * p.dense_pitch + td.dense_off + threadIdx.x * 128);
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    if ((pl[w][0] | pl[w][1] | pl[w][2] | pl[w][3] | pl[w][4] | pl[w][5] | pl[w][6] |
+                         pl[w][7]) == 0)
+                        continue;   // sparse data: most words saw no hit in a short chunk
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        const uint32_t pk = planes_pack4(pl[w], g);
+                        const uint32_t a = (pk & 0xFFu) | ((pk & 0xFF00u) << 8);
+                        const uint32_t b = ((pk >> 16) & 0xFFu) | ((pk >> 24) << 16);
+                        if (a) atomicAdd(dst + 16 * w + 2 * g, a);
+                        if (b) atomicAdd(dst + 16 * w + 2 * g + 1, b);
+                    }
+                }
+            }
+        } else if (MODE == MODE_DENSE8 || MODE == MODE_DENSE16 || MODE == MODE_DENSE32) {
             flush_dense();
         } else {
             // threshold in bit-sliced form, then append the survivors as sort keys

@@ -250,6 +250,12 @@ struct FinalizeParams {
     uint32_t stride;
     uint32_t fin_sort_max;     // keys the CTA sort may hold (<= FIN_SORT_MAX, power of two)
     uint32_t large_in_scratch;
+    // small batches (nq <= FIN_WARPS, one CTA): CSR formatting fused in -- offsets, keys and the
+    // batch's invalid-base flag land in the result area without two more launches
+    uint64_t* csr_off;         // optional [nq + 1]
+    uint64_t* csr_keys;
+    const int* flags_src;
+    int* flags_dst;
 };
 
 __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(FinalizeParams p) {
@@ -331,6 +337,29 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(FinalizeParams
         __syncthreads();
     }
     (void)in_place;
+    if (p.csr_off != nullptr) {   // (host guarantees gridDim.x == 1 and nq <= FIN_WARPS)
+        __shared__ uint64_t off_s[FIN_WARPS + 1];
+        __syncthreads();          // the lists and counts of this CTA are complete
+        if (threadIdx.x == 0) {
+            uint64_t run = 0;
+            for (uint32_t i = 0; i < p.nq; ++i) {
+                off_s[i] = run;
+                const uint32_t c = p.out_counts[i];
+                run += c >= COUNT_INVALID ? 0 : c;
+            }
+            off_s[p.nq] = run;
+            for (uint32_t i = 0; i <= p.nq; ++i) p.csr_off[i] = off_s[i];
+            p.flags_dst[0] = p.flags_src[0];
+            p.flags_dst[1] = p.flags_src[1];
+        }
+        __syncthreads();
+        if (q < p.nq) {
+            const uint32_t c = static_cast<uint32_t>(off_s[warp + 1] - off_s[warp]);
+            const uint64_t* src = p.out_keys + static_cast<uint64_t>(q) * p.stride;
+            uint64_t* dst = p.csr_keys + off_s[warp];
+            for (uint32_t i = lane; i < c; i += 32) dst[i] = src[i];
+        }
+    }
 }
 
 // CSR formatting of finalized lists: keys of slot qi (sorted in place at cand[qi * cap], count

@@ -236,3 +236,21 @@ def test_exhaustive_lists_counting_sort(kind, n_docs, sig, h, ps):
     for q, r in zip(qs, g.search_batch(qs, 0.0, 0)):
         assert as_list(r) == oracle.search(o, q, 0.0, 0)
     g.close()
+
+
+@pytest.mark.parametrize("kind,n_docs,sig,h,ps", [
+    (KIND_CLASSIC, 70000, [53], 3, 0), (KIND_COMPACT, 40000, [61, 97, 31, 43, 59], 3, 1024),
+    (KIND_CLASSIC, 129, [333], 4, 0),
+])
+def test_few_long_queries_take_the_k_split_kernel(kind, n_docs, sig, h, ps):
+    """one or a few long queries (a gene against the index): their k-mers are split into chunks
+    that become work items of their own; counts are accumulated with packed atomics"""
+    g, o = pair(kind, n_docs, sig, h, page_size=ps, seed=n_docs + 21)
+    for lens in ([286], [1030], [10_030], [300, 5000, 100, 2000], [40_000, 31]):
+        qs = [rq(1000 + i + lens[0], L) for i, L in enumerate(lens)]
+        if h == 1:
+            qs = [q for q in qs if len(q) > 31]
+        for thr, k in ((0.0, 10), (0.3, 0), (0.0, 0), (0.8, 0), (0.01, 2000)):
+            for q, r in zip(qs, g.search_batch(qs, thr, k)):
+                assert as_list(r) == oracle.search(o, q, thr, k), (lens, thr, k)
+    g.close()
