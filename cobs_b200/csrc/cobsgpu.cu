@@ -508,12 +508,26 @@ void build_layout(cobsgpu_index* ix, const std::vector<uint64_t>& sig) {
             lp.doc_base = static_cast<uint32_t>(8 * b0);
             ix->pages.push_back(lp);
         }
+    } else if (div_ceil<uint64_t>(ps, 16) >= 4ull * S) {
+        // Compact, pages wide enough: every shard holds the SAME column range of EVERY page (cut
+        // at multiples of 128 documents, at least 64 bytes per page and shard).  Work per k-mer
+        // (h * bytes) and memory are then equal across shards to within one granule -- dealing
+        // out whole pages (below) left 77 pages over 8 shards at 9 or 10 pages, and the step
+        // waits for the shards with 10.
+        const uint64_t gran = div_ceil<uint64_t>(ps, 16);
+        const uint64_t lo = gran * g / S, hi = gran * (g + 1) / S;
+        const uint64_t b0 = lo * 16, b1 = std::min<uint64_t>(hi * 16, ps);
+        for (uint32_t p = 0; p < P && b1 > b0; ++p) {
+            LocalPage lp{};
+            lp.global_page = p;
+            lp.sig = sig[p];
+            lp.byte_begin = b0;
+            lp.row_bytes = static_cast<uint32_t>(b1 - b0);
+            lp.doc_base = static_cast<uint32_t>(static_cast<uint64_t>(p) * 8 * ps + 8 * b0);
+            ix->pages.push_back(lp);
+        }
     } else {
-        // Whole pages per shard.  Every page costs the same per query k-mer (h * page_size bytes,
-        // whatever its signature_size), while its memory is signature_size * page_size: pages are
-        // sorted by size and dealt out in serpentine order, which balances the page COUNT
-        // (= work) to +-1 and the bytes (= HBM) closely.  Page sets are not contiguous; results
-        // carry global document ids, so nothing downstream cares.
+        // Narrow pages: whole pages per shard.  Every page costs the same per query k-mer
         std::vector<uint32_t> order(P);
         for (uint32_t p = 0; p < P; ++p) order[p] = p;
         std::stable_sort(order.begin(), order.end(),

@@ -74,8 +74,9 @@ typedef struct cobsgpu_index_desc {
     uint64_t fill_seed;
     int32_t device;             /* CUDA device ordinal */
     /* document-axis shard held by this handle: shard_index of shard_count.
-     * Classic: contiguous column ranges cut at multiples of 128 documents; compact: whole
-     * pages, dealt out so that page count (work) and bytes (HBM) are both balanced.
+     * Classic: contiguous column ranges cut at multiples of 128 documents; compact: the same
+     * column range of every page (pages of >= 64 bytes per shard), else whole pages dealt out
+     * so that page count (work) and bytes (HBM) are both balanced.
      * Results carry GLOBAL document ids. */
     uint32_t shard_index;
     uint32_t shard_count;

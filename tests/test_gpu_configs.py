@@ -7,7 +7,8 @@ cfg1  literally: the reference's own `classic_construct_random` builds the 128-d
       the reference's own `cobs query` binary.
 cfg3  at the size bench.py times (196 613-row base, 158.7 GB).
 cfg5  per-shard parity: shards 0, 3 and 7 of the 8-way document split of the 10 M-document,
-      77-page compact index (75 GB each), sampled column blocks against the procedural oracle.
+      77-page compact index (75 GB each; every shard holds one 2048-byte column slice of every
+      page), sampled column blocks against the procedural oracle.
 """
 import os
 import subprocess
@@ -133,32 +134,30 @@ def test_cfg3_compact_at_the_benched_size():
 
 @pytest.mark.parametrize("shard", [0, 3, 7])
 def test_cfg5_shard_parity(shard):
-    """one of the eight document shards of cfg5 (whole pages, ~75 GB) on one GPU"""
+    """one of the eight document shards of cfg5 on one GPU (~75 GB): the shard holds the same
+    2048-byte column slice (16 384 documents) of each of the 77 pages"""
     n_docs, ps, h = 10_000_000, 16_384, 4
     sig = [int(100_003 * 1.0345 ** p) for p in range(77)]
     g = open_or_skip(KIND_COMPACT, n_docs, sig, h, page_size=ps, fill_seed=SEED,
                      shard_index=shard, shard_count=8)
     o = oracle.Index.procedural(oracle.KIND_COMPACT, n_docs, sig, h, page_size=ps, fill_seed=SEED)
-    per_page = 8 * ps
-    # the pages of this shard: where the scores come back non-trivially; sample blocks in the
-    # first, a middle and the last page held, plus the ragged end of the index
+    per_page, per_slice = 8 * ps, 8 * ps // 8
+    assert g.info.bytes_per_kmer == h * 77 * (ps // 8)
     q = [oracle.random_query(50 + shard, 100)]
     a = g.scores(q)[0]
-    # pages not held by this shard are left untouched (zero); find the held ones from the oracle
-    held = []
-    for p in range(77):
-        b0 = p * per_page + 512
-        want = o.scores(q[0], b0, b0 + 256)
-        if np.array_equal(a[b0:b0 + 256], want) and want.any():
-            held.append(p)
-    assert 9 <= len(held) <= 10            # 77 pages dealt out over 8 shards
-    for p in (held[0], held[len(held) // 2], held[-1]):
-        for b0 in (p * per_page, p * per_page + per_page // 2, (p + 1) * per_page - 1024):
+    other = (shard + 1) % 8
+    for p in (0, 38, 76):
+        s0 = p * per_page + shard * per_slice
+        for b0 in (s0, s0 + per_slice // 2, s0 + per_slice - 1024):
             b1 = min(b0 + 1024, o.counts_size)
             assert np.array_equal(a[b0:b1], o.scores(q[0], b0, b1)), (p, b0)
+        # columns of another shard are left untouched
+        o0 = p * per_page + other * per_slice
+        assert not a[o0:o0 + 1024].any()
     # lists of this shard: global document ids, only real documents, ordered
     doc, score = g.search_batch(q, 0.07, 0)[0]
-    keep = [d for d in np.nonzero(a[:n_docs] >= 5)[0].tolist() if d // per_page in held]
+    mine = (np.arange(o.counts_size) % per_page) // per_slice == shard
+    keep = np.nonzero((a[:n_docs] >= 5) & mine[:n_docs])[0].tolist()
     order = sorted(keep, key=lambda d: (-int(a[d]), d))
     assert doc.tolist() == order and score.tolist() == [int(a[d]) for d in order]
     g.close()

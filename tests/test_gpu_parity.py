@@ -263,7 +263,8 @@ def test_python_known_answer():
 @pytest.mark.parametrize("shards", [2, 3, 8])
 def test_shards_partition_columns(shards):
     for kind, n_docs, sig, ps in ((KIND_CLASSIC, 5000, [37], 0),
-                                  (KIND_COMPACT, 1500, [23, 41, 19, 33, 27], 40)):
+                                  (KIND_COMPACT, 1500, [23, 41, 19, 33, 27], 40),      # whole pages
+                                  (KIND_COMPACT, 30000, [23, 41, 19, 33], 1024)):      # column slices
         _, o = pair(kind, n_docs, sig, 3, page_size=ps, seed=12)
         queries = [rq(i, L) for i, L in enumerate([100, 90, 286])]
         acc = np.zeros((len(queries), o.counts_size), dtype=np.uint32)
