@@ -1531,7 +1531,8 @@ Slot& submit_batch(cobsgpu_index* ix, const char* queries, const uint64_t* offse
     // A few LONG queries (a gene or a plasmid against the index): with one work item per (query,
     // tile) only n_tiles CTAs would run, each walking a latency chain of thousands of k-mers.
     // Such batches take the k-split score kernel + the dense counting sort at collect instead.
-    sl.ksplit = sl.huge_ids.empty() && main_max_T >= 256 &&
+    static const bool no_ksplit = std::getenv("COBSGPU_NO_KSPLIT") != nullptr;   // experiments only
+    sl.ksplit = !no_ksplit && sl.huge_ids.empty() && main_max_T >= 256 &&
                 static_cast<uint64_t>(n_main) * ix->tiles.size() < 2ull * 3 * ix->sm_count;
     if (n_main == 0 || sl.ksplit || !plan_main_pass(ix, sl, threshold, limit, main_max_T, &pl)) {
         // exhaustive at collect; only the invalid-base flag is needed from the device
