@@ -1269,8 +1269,12 @@ const uint32_t* upload_qlist(Slot& work, const std::vector<uint32_t>& ids, size_
 // One sub-batch of the exhaustive path for queries of at most 65 535 k-mers: K2 stores one count
 // per document (DENSE8 / DENSE16), then a stable multi-CTA counting sort on the score
 // (densesort.cuh) writes the ordered keys straight into the CSR area of work.d_out.
-void exhaustive_dense(cobsgpu_index* ix, const Slot& src, Slot& work, const uint32_t* d_ql,
-                      uint32_t n, uint32_t max_T, uint64_t limit, bool ksplit, cudaStream_t st) {
+// Returns the candidate slots per query when the k-split reduce emitted thresholded candidates
+// (the header's cand_count words then tell whether a query overflowed them and stage 1 -- the
+// counting sort over the dense vector that is still there -- has to follow), else 0.
+uint32_t exhaustive_dense(cobsgpu_index* ix, const Slot& src, Slot& work, const uint32_t* d_ql,
+                          uint32_t n, uint32_t max_T, uint64_t limit, bool ksplit, int stage,
+                          cudaStream_t st) {
     // k-split: the k-mers of every query are cut into chunks that become work items of their own
     // (partial counts added into the u16 vector), sized so that the items fill the GPU
     uint32_t kchunk = 0, n_kchunks = 1;
@@ -1282,6 +1286,10 @@ void exhaustive_dense(cobsgpu_index* ix, const Slot& src, Slot& work, const uint
         n_kchunks = div_ceil<uint32_t>(max_T, kchunk);
         if (n_kchunks <= 1) ksplit = false;
     }
+    if (ksplit) {
+        // one dense8 vector per (query, chunk), summed into the u16 vector afterwards
+        work.d_scratch.ensure(static_cast<uint64_t>(n) * n_kchunks * ix->dense_pitch);
+    }
     const bool two = ksplit || max_T > MAX_T_SHORT;
     const uint32_t cap = std::max<uint32_t>(ix->shard_real_docs, 1);
     const size_t esz = two ? 2 : 1;
@@ -1292,17 +1300,61 @@ void exhaustive_dense(cobsgpu_index* ix, const Slot& src, Slot& work, const uint
     work.d_total.ensure(static_cast<size_t>(n) * 8);
     uint32_t* total1 = work.d_total.as<uint32_t>();
     uint32_t* total2 = total1 + n;
-    CK(cudaMemsetAsync(work.d_dense.p, 0, static_cast<uint64_t>(n) * ix->dense_pitch * esz, st));
-    CK(cudaMemsetAsync(work.o_cc(), 0, static_cast<size_t>(n) * 4, st));   // (no candidate slots here)
+    const uint32_t np = static_cast<uint32_t>(ix->pages.size());
     ScoreParams sp = base_params(ix, src, d_ql, n);
     sp.dense8 = work.d_dense.as<uint8_t>();
     sp.dense16 = work.d_dense.as<uint16_t>();
-    sp.kchunk = kchunk;
-    sp.n_kchunks = n_kchunks;
-    launch_score(ix, sp, ksplit ? MODE_KSPLIT : (two ? MODE_DENSE16 : MODE_DENSE8), two, st);
+    CK(cudaMemsetAsync(work.o_cc(), 0, static_cast<size_t>(n) * 4, st));
+    if (stage == 0) {
+        if (!ksplit)
+            CK(cudaMemsetAsync(work.d_dense.p, 0, static_cast<uint64_t>(n) * ix->dense_pitch * esz, st));
+        sp.kchunk = kchunk;
+        sp.n_kchunks = n_kchunks;
+        if (ksplit) sp.dense8 = work.d_scratch.as<uint8_t>();
+        launch_score(ix, sp, ksplit ? MODE_KSPLIT : (two ? MODE_DENSE16 : MODE_DENSE8), two, st);
+        sp.dense8 = work.d_dense.as<uint8_t>();
+        if (ksplit && !ix->pages.empty()) {
+            // threshold > 0: the reduce appends the documents that pass, like the CAND epilogue
+            const bool emit = src.threshold > 0.0;
+            const uint32_t ccap = std::min<uint32_t>(ix->max_candidates, cap);
+            KsplitReduceParams rp{};
+            rp.part8 = work.d_scratch.as<uint8_t>();
+            rp.out16 = work.d_dense.as<uint16_t>();
+            rp.dense_pitch = ix->dense_pitch;
+            rp.koff = src.d_koff();
+            rp.qlist = d_ql;
+            rp.kchunk = kchunk;
+            rp.n_kchunks = n_kchunks;
+            if (emit) {
+                work.d_cand.ensure(static_cast<uint64_t>(n) * ccap * 8);
+                work.d_res_count.ensure(static_cast<size_t>(n) * 4);
+                rp.thr = src.d_thr();
+                rp.seg_dense_off = ix->d_seg;
+                rp.seg_n_real = ix->d_seg + np;
+                rp.seg_doc_base = ix->d_seg + 2 * np;
+                rp.n_seg = np;
+                rp.cand_count = work.o_cc();
+                rp.cand = work.d_cand.as<uint64_t>();
+                rp.cap = ccap;
+            }
+            const dim3 rgrid(div_ceil<uint32_t>(static_cast<uint32_t>(ix->dense_pitch), 256 * 16), n);
+            ksplit_reduce_kernel<<<rgrid, 256, 0, st>>>(rp);
+            CK(cudaGetLastError());
+            ix->tm.kernel_launches++;
+            if (emit) {
+                PassPlan cp;
+                cp.mode = MODE_CAND;
+                cp.cap = ccap;
+                cp.limit = limit;
+                launch_select(ix, src, work, d_ql, n, cp, max_T, work.o_cc(), work.d_cand.as<uint64_t>(),
+                              work.d_res_count.as<uint32_t>(), ccap, false, st);
+                launch_csr(ix, src, work, n, ccap, st);
+                return ccap;
+            }
+        }
+    }
 
     PhaseScope ps(ix, PH_SELECT, st);
-    const uint32_t np = static_cast<uint32_t>(ix->pages.size());
     DenseSortParams dp{};
     dp.dense8 = sp.dense8;
     dp.dense16 = sp.dense16;
@@ -1352,6 +1404,7 @@ void exhaustive_dense(cobsgpu_index* ix, const Slot& src, Slot& work, const uint
         final_pass(total2);
     }
     CK(cudaMemcpyAsync(work.o_flags(), src.d_flags(), 8, cudaMemcpyDeviceToDevice, st));
+    return 0;
 }
 
 // Synchronous exhaustive pass over the given queries of the batch in `src`, in workspace-bounded
@@ -1382,6 +1435,7 @@ void run_exhaustive(cobsgpu_index* ix, const Slot& src, const std::vector<uint32
         } else {
             const uint64_t n_chunks = div_ceil<uint64_t>(std::max<uint64_t>(ix->dense_pitch, pl.cap), DS_CHUNK);
             per_q = ix->dense_pitch * 2 + n_chunks * 1024 + out_per_q + static_cast<uint64_t>(pl.cap) * 8;
+            if (ksplit) per_q += ix->dense_pitch * 64;   // (chunk vectors; a k-split batch is a few queries)
         }
         const size_t sub = static_cast<size_t>(
             std::max<uint64_t>(1, std::min<uint64_t>(list.size(), ix->workspace_bytes / std::max<uint64_t>(per_q, 1))));
@@ -1394,8 +1448,9 @@ void run_exhaustive(cobsgpu_index* ix, const Slot& src, const std::vector<uint32
             pl.lng = max_T > MAX_T_SHORT;
             pl.mode = MODE_DENSE32;
             work.d_out.ensure(out_bytes(work, n, pl));
+            uint32_t cand_cap = 0;
             if (!huge) {
-                exhaustive_dense(ix, src, work, d_ql, n, max_T, limit, ksplit, st);
+                cand_cap = exhaustive_dense(ix, src, work, d_ql, n, max_T, limit, ksplit, 0, st);
             } else {
                 work.d_res_count.ensure(static_cast<size_t>(n) * 4);
                 launch_pass_score(ix, src, work, d_ql, n, pl, work.o_cc(), st);
@@ -1410,6 +1465,18 @@ void run_exhaustive(cobsgpu_index* ix, const Slot& src, const std::vector<uint32
                 CK(cudaMemcpyAsync(work.h_out.p, work.d_out.p, work.out_keys, cudaMemcpyDeviceToHost, st));
             }
             CK(cudaStreamSynchronize(st));
+            if (cand_cap) {
+                // k-split batch with a threshold: did a query overflow its candidate slots?  Then
+                // the counting sort over the dense vector (still there) produces the lists.
+                const uint32_t* cc = reinterpret_cast<const uint32_t*>(work.h_out.as<char>() + work.out_cc);
+                bool over = false;
+                for (uint32_t i = 0; i < n; ++i) over = over || cc[i] > cand_cap;
+                if (over) {
+                    exhaustive_dense(ix, src, work, d_ql, n, max_T, limit, ksplit, 1, st);
+                    CK(cudaMemcpyAsync(work.h_out.p, work.d_out.p, work.out_keys, cudaMemcpyDeviceToHost, st));
+                    CK(cudaStreamSynchronize(st));
+                }
+            }
             lists->emplace_back();
             HostList& L = lists->back();
             const uint64_t* off = reinterpret_cast<const uint64_t*>(work.h_out.as<char>() + work.out_off);
@@ -1524,16 +1591,30 @@ Slot& submit_batch(cobsgpu_index* ix, const char* queries, const uint64_t* offse
     const uint32_t n_main = sl.huge_ids.empty() ? nq : static_cast<uint32_t>(sl.main_ids.size());
     PassPlan pl;
     sl.mode = -1;
-    sl.busy = true;
-    sl.ticket = ++ix->ticket_counter;
+    // the slot only becomes a ticket once everything below has been enqueued: an error on the
+    // way (a CUDA failure, an allocation) must not leave it marked busy for ever
+    struct Commit {
+        cobsgpu_index* ix;
+        Slot& sl;
+        bool ok = false;
+        ~Commit() {
+            if (!ok) return;
+            sl.busy = true;
+            sl.ticket = ++ix->ticket_counter;
+        }
+    } commit{ ix, sl };
     cudaStream_t st = ix->stream;
     if (!small) CK(cudaStreamWaitEvent(st, sl.ev_in, 0));
     // A few LONG queries (a gene or a plasmid against the index): with one work item per (query,
     // tile) only n_tiles CTAs would run, each walking a latency chain of thousands of k-mers.
     // Such batches take the k-split score kernel + the dense counting sort at collect instead.
     static const bool no_ksplit = std::getenv("COBSGPU_NO_KSPLIT") != nullptr;   // experiments only
+    // (measured: an unsplit item walks ~0.18 us per k-mer; the split path costs ~40 us of extra
+    // launches plus, without a threshold, a counting sort of ~0.3 us per 1000 documents -- split
+    // only when the chain is clearly longer)
     sl.ksplit = !no_ksplit && sl.huge_ids.empty() && main_max_T >= 256 &&
-                static_cast<uint64_t>(n_main) * ix->tiles.size() < 2ull * 3 * ix->sm_count;
+                static_cast<uint64_t>(n_main) * ix->tiles.size() < 2ull * 3 * ix->sm_count &&
+                0.18 * main_max_T > 1.3 * (40.0 + (threshold > 0.0 ? 0.00002 : 0.0003) * ix->shard_real_docs);
     if (n_main == 0 || sl.ksplit || !plan_main_pass(ix, sl, threshold, limit, main_max_T, &pl)) {
         // exhaustive at collect; only the invalid-base flag is needed from the device
         sl.layout_out(0);
@@ -1541,6 +1622,7 @@ Slot& submit_batch(cobsgpu_index* ix, const char* queries, const uint64_t* offse
         sl.h_out.ensure(sl.out_keys);
         CK(cudaMemcpyAsync(sl.h_out.p, sl.d_flags(), 8, cudaMemcpyDeviceToHost, st));
         CK(cudaEventRecord(sl.ev(sl.ev_out), st));
+        commit.ok = true;
         return sl;
     }
     sl.mode = pl.mode;
@@ -1569,6 +1651,7 @@ Slot& submit_batch(cobsgpu_index* ix, const char* queries, const uint64_t* offse
                            st_out));
     }
     CK(cudaEventRecord(sl.ev(sl.ev_out), st_out));
+    commit.ok = true;
     return sl;
 }
 

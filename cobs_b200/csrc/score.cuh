@@ -35,10 +35,11 @@
 //                                  contains the query's global top-k, never overflows, and is
 //                                  tiny, so `-t 0 -l k` no longer materialises every document.
 //                         KSPLIT -> a work item is (query, tile, CHUNK of the query's k-mers): the
-//                                  partial counts of the chunk are added into a u16 score vector
-//                                  with packed atomics.  For a few long queries (one gene against
-//                                  the index) the chunks spread one query over every SM instead of
-//                                  leaving it to n_tiles CTAs whose k-mers form a latency chain.
+//                                  partial counts of the chunk are stored as bytes in the chunk's
+//                                  own vector and summed by ksplit_reduce_kernel.  For a few long
+//                                  queries (one gene against the index) the chunks spread one query
+//                                  over every SM instead of leaving it to n_tiles CTAs whose k-mers
+//                                  form a latency chain.
 //   * NP = number of bit-planes per word: 8 (queries of <= 255 k-mers) or 16 (<= 65 535).
 #pragma once
 
@@ -326,9 +327,9 @@ __global__ void __launch_bounds__(SCORE_MAX_THREADS, 3) score_kernel(const Score
         // transposes the planes into per-document counts: store (DENSE8) or add (DENSE32)
         auto flush_dense = [&]() {
             if (!active) return;
-            const uint64_t col = static_cast<uint64_t>(qi) * p.dense_pitch + td.dense_off +
-                                 threadIdx.x * 128;
-            if (MODE == MODE_DENSE8) {
+            const uint64_t slot = MODE == MODE_KSPLIT ? static_cast<uint64_t>(qi) * p.n_kchunks + kc : qi;
+            const uint64_t col = slot * p.dense_pitch + td.dense_off + threadIdx.x * 128;
+            if (MODE == MODE_DENSE8 || MODE == MODE_KSPLIT) {
                 uint4* dst = reinterpret_cast<uint4*>(p.dense8 + col);
 #pragma unroll
                 for (int w = 0; w < 4; ++w) {
@@ -463,26 +464,11 @@ __global__ void __launch_bounds__(SCORE_MAX_THREADS, 3) score_kernel(const Score
         }
 
         if (MODE == MODE_KSPLIT) {
-            // partial counts of this chunk (<= 248) -> packed u16 adds, two documents per atomic;
-            // the sums stay below 65 536, so no carry crosses the halves
-            if (active && T != 0) {
-                uint32_t* dst = reinterpret_cast<uint32_t*>(
-                    p.dense16 + static_cast<uint64_t>(qi) * p.dense_pitch + td.dense_off + threadIdx.x * 128);
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    if ((pl[w][0] | pl[w][1] | pl[w][2] | pl[w][3] | pl[w][4] | pl[w][5] | pl[w][6] |
-                         pl[w][7]) == 0)
-                        continue;   // sparse data: most words saw no hit in a short chunk
-#pragma unroll
-                    for (int g = 0; g < 8; ++g) {
-                        const uint32_t pk = planes_pack4(pl[w], g);
-                        const uint32_t a = (pk & 0xFFu) | ((pk & 0xFF00u) << 8);
-                        const uint32_t b = ((pk >> 16) & 0xFFu) | ((pk >> 24) << 16);
-                        if (a) atomicAdd(dst + 16 * w + 2 * g, a);
-                        if (b) atomicAdd(dst + 16 * w + 2 * g + 1, b);
-                    }
-                }
-            }
+            // partial counts of this chunk (<= 248 fit a byte) go to the chunk's own dense8 vector,
+            // slot qi * n_kchunks + kc; ksplit_reduce_kernel adds the chunks up afterwards.  (A
+            // first version added into one u16 vector with packed atomics: 20 M atomics for one
+            // 10 000-k-mer query on a million documents cost more than the row traffic.)
+            if (T != 0) flush_dense();
         } else if (MODE == MODE_DENSE8 || MODE == MODE_DENSE16 || MODE == MODE_DENSE32) {
             flush_dense();
         } else {
@@ -592,5 +578,103 @@ __global__ void __launch_bounds__(SCORE_MAX_THREADS, 3) score_kernel(const Score
 }
 
 #undef COBS_CSA
+
+// Sums the per-chunk byte counts of MODE_KSPLIT into the u16 score vector of each query:
+// out16[q][c] = sum over the chunks kc < ceil(T_q / kchunk) of part8[(q * n_kchunks + kc)][c].
+// grid (dense_pitch / (256 * 16), n_slots); a thread owns 16 columns.
+struct KsplitReduceParams {
+    const uint8_t* part8;     // [n_slots * n_kchunks][dense_pitch]
+    uint16_t* out16;          // [n_slots][dense_pitch]
+    uint64_t dense_pitch;     // multiple of 128
+    const uint32_t* koff;     // [nq + 1]
+    const uint32_t* qlist;    // optional: slot -> batch query
+    uint32_t kchunk, n_kchunks;
+    // optional fused threshold (threshold > 0): documents with score >= thr[q] are appended as
+    // sort keys right here, so a batch with few hits never needs the counting sort over all
+    // documents; cand == nullptr switches it off
+    const uint32_t* thr;             // [nq] by batch query
+    const uint32_t* seg_dense_off;   // page segments of the dense layout
+    const uint32_t* seg_n_real;
+    const uint32_t* seg_doc_base;
+    uint32_t n_seg;
+    uint32_t* cand_count;            // [n_slots]
+    uint64_t* cand;                  // [n_slots * cap]
+    uint32_t cap;
+};
+
+__global__ void __launch_bounds__(256) ksplit_reduce_kernel(KsplitReduceParams p) {
+    const uint32_t slot = blockIdx.y;
+    const uint64_t c0 = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 16;
+    // (threads past the end stay for the warp-wide append below)
+    const bool in_range = c0 < p.dense_pitch;
+    const uint32_t q = p.qlist ? p.qlist[slot] : slot;
+    const uint32_t T = p.koff[q + 1] - p.koff[q];
+    const uint32_t chunks = (T + p.kchunk - 1) / p.kchunk;   // chunks this query really has
+    uint32_t acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0;
+    if (in_range) {
+        for (uint32_t kc = 0; kc < chunks && kc < p.n_kchunks; ++kc) {
+            const uint4 v = *reinterpret_cast<const uint4*>(
+                p.part8 + (static_cast<uint64_t>(slot) * p.n_kchunks + kc) * p.dense_pitch + c0);
+            const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] += (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+        }
+        uint4 lo, hi;
+        lo.x = acc[0] | (acc[1] << 16);
+        lo.y = acc[2] | (acc[3] << 16);
+        lo.z = acc[4] | (acc[5] << 16);
+        lo.w = acc[6] | (acc[7] << 16);
+        hi.x = acc[8] | (acc[9] << 16);
+        hi.y = acc[10] | (acc[11] << 16);
+        hi.z = acc[12] | (acc[13] << 16);
+        hi.w = acc[14] | (acc[15] << 16);
+        uint4* dst = reinterpret_cast<uint4*>(p.out16 + static_cast<uint64_t>(slot) * p.dense_pitch + c0);
+        dst[0] = lo;
+        dst[1] = hi;
+    }
+    if (p.cand == nullptr) return;
+    uint32_t mask = 0, doc0 = 0;
+    if (in_range) {
+        // the 16 columns of a thread lie in one page segment (segments start at multiples of 128)
+        uint32_t lo_s = 0, hi_s = p.n_seg;
+        while (hi_s - lo_s > 1) {
+            const uint32_t mid = (lo_s + hi_s) >> 1;
+            if (p.seg_dense_off[mid] <= c0) lo_s = mid;
+            else hi_s = mid;
+        }
+        const uint32_t rel0 = static_cast<uint32_t>(c0) - p.seg_dense_off[lo_s];
+        const uint32_t n_real = p.seg_n_real[lo_s];
+        doc0 = p.seg_doc_base[lo_s] + rel0;
+        const uint32_t thr = p.thr[q];
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (rel0 + i < n_real && acc[i] >= thr) mask |= 1u << i;
+    }
+    // warp-aggregated append
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t cnt = __popc(mask);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    if (total == 0) return;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&p.cand_count[slot], total);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    uint32_t pos = base + incl - cnt;
+    uint64_t* out = p.cand + static_cast<uint64_t>(slot) * p.cap;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        if ((mask >> i) & 1u) {
+            if (pos < p.cap) out[pos] = make_key(acc[i], doc0 + i);
+            ++pos;
+        }
+    }
+}
 
 }  // namespace cobsgpu
