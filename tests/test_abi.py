@@ -77,7 +77,8 @@ def test_bad_files_are_rejected_before_touching_the_gpu(tmp_path):
 def test_product_does_not_import_the_oracle():
     """the oracle is test infrastructure: nothing under cobs_b200/ may reference it"""
     bad = []
-    for dirpath, _, files in os.walk(os.path.join(ROOT, "cobs_b200")):
+    walk = list(os.walk(os.path.join(ROOT, "cobs_b200"))) + list(os.walk(os.path.join(ROOT, "cobs_index")))
+    for dirpath, _, files in walk:
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
