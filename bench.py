@@ -535,6 +535,11 @@ def run_workload(env, wl, primary, parallelism):
                 d2h[0] = roff.nbytes + doc.nbytes + score.nbytes
             depth = 3
         else:
+            if not args.no_overlap:
+                # upload + K1 of batch i+1 run ahead on the library's input stream
+                index.set_option("prefetch", 1)
+                index.set_option("inputs_ready", 0)
+
             def submit(i):
                 return search.submit_host(pinned[i], off, thr, limit)
 
@@ -559,6 +564,8 @@ def run_workload(env, wl, primary, parallelism):
         env.torch.cuda.synchronize()
         dt = env.max_over_ranks(time.perf_counter() - t0)
         env.barrier()
+        if world > 1:
+            index.set_option("prefetch", 0)
         return {"value": nq * T_KMERS * steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": int(env.max_over_ranks(d2h[0]))}
 

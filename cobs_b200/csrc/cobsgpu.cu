@@ -358,7 +358,8 @@ struct cobsgpu_index {
     Slot aux;                             // workspace of the exhaustive passes / cobsgpu_scores
     int next_slot = 0;
     uint64_t ticket_counter = 0;
-    bool prefetch = false, inputs_ready = false;
+    bool prefetch = false, inputs_ready = false, input_stream_set = false;
+    cudaStream_t input_stream = nullptr;  // device path: where the caller uploads d_queries
     cudaEvent_t ev_caller = nullptr;      // device path: caller's stream -> s_in ordering
     // cached launch configuration of the score kernel per mode
     struct ScoreCfg {
@@ -2405,6 +2406,11 @@ int cobsgpu_set_option(cobsgpu_index* ix, const char* name, int64_t value) {
         else if (n == "timing") ix->timing = value != 0;
         else if (n == "prefetch") ix->prefetch = value != 0;
         else if (n == "inputs_ready") ix->inputs_ready = value != 0;
+        else if (n == "input_stream") {
+            // a cudaStream_t passed as an integer; -1 = back to the caller's compute stream
+            ix->input_stream_set = value != -1;
+            ix->input_stream = value == -1 ? nullptr : reinterpret_cast<cudaStream_t>(static_cast<intptr_t>(value));
+        }
         else throw Err{ COBSGPU_ERR_INVALID_ARG, "unknown option or bad value: " + n };
     });
 }
@@ -2705,9 +2711,13 @@ int cobsgpu_search_batch_device(cobsgpu_index* ix, const char* d_queries, const 
         cudaStream_t ks = st;
         if (ix->prefetch) {
             ks = ix->s_in;
-            if (!ix->inputs_ready) {   // d_queries may still be produced on the caller's stream
+            if (!ix->inputs_ready) {
+                // d_queries may still be in the making: on the stream named by the "input_stream"
+                // option (an upload stream of the caller's, so that K1 does not queue behind the
+                // previous batch's K2 on the caller's compute stream), else on `stream` itself
+                cudaStream_t src = ix->input_stream_set ? ix->input_stream : st;
                 if (!ix->ev_caller) CK(cudaEventCreateWithFlags(&ix->ev_caller, cudaEventDisableTiming));
-                CK(cudaEventRecord(ix->ev_caller, st));
+                CK(cudaEventRecord(ix->ev_caller, src));
                 CK(cudaStreamWaitEvent(ks, ix->ev_caller, 0));
             }
             // the slot's previous K2/K3 (N_SLOTS calls ago) must have finished with its buffers

@@ -190,7 +190,10 @@ const char* cobsgpu_index_doc_name(const cobsgpu_index* idx, uint32_t doc);
  * "prefetch" (0/1: cobsgpu_search_batch_device runs the metadata upload + K1 of a call on an
  * internal stream, double-buffered, so that they overlap the previous call's K2),
  * "inputs_ready" (0/1: with prefetch, the caller guarantees d_queries is already complete --
- * otherwise the internal stream first waits for the caller's stream) */
+ * otherwise the internal stream first waits for the caller's stream),
+ * "input_stream" (with prefetch and inputs_ready 0: the cudaStream_t, passed as an integer, on
+ * which the caller uploads d_queries -- K1 then waits for that stream instead of queueing
+ * behind the caller's compute stream; -1 = none) */
 int cobsgpu_set_option(cobsgpu_index* idx, const char* name, int64_t value);
 
 /*
