@@ -14,6 +14,7 @@
 #include <memory>
 #include <sstream>
 #include <string>
+#include <vector>
 
 static int g_failed = 0;
 #define CHECK(cond)                                                               \
@@ -133,6 +134,67 @@ int main(int argc, char** argv) {
         }
         catch (const DieException& e) {
             threw = std::string(e.what()).find("Could not open index path") != std::string::npos;
+        }
+        CHECK(threw);
+    }
+
+    // the plug point for custom row sources: an index handed over as in-memory pages
+    // (HbmIndexSearchFile::Pages) behaves like the file it was read from; a foreign
+    // IndexSearchFile subclass is refused with a message instead of being searched wrongly
+    {
+        // rebuild all160.cobs_classic from rows read back through read_from_disk()
+        auto file = std::make_shared<ClassicIndexMMapSearchFile>(dir + "/all160.cobs_classic");
+        const uint64_t row = file->row_size();
+        // signature size is not part of the interface: probe rows 0..S-1 via raw hashes
+        // (hash % S == hash for hash < S); S comes from the file size here
+        std::FILE* f = std::fopen((dir + "/all160.cobs_classic").c_str(), "rb");
+        std::fseek(f, 0, SEEK_END);
+        const long size = std::ftell(f);
+        std::fclose(f);
+        // header: magic(5+13) version(4) term(4) canon(1) n_docs(4) sig(8) hashes(8) names... magic(13)
+        size_t names = 0;
+        for (auto& n : file->file_names()) names += n.size() + 1;
+        const uint64_t S = (uint64_t(size) - (5 + 13 + 4 + 4 + 1 + 4 + 8 + 8 + names + 13)) / row;
+        std::vector<size_t> hashes(S);
+        for (uint64_t i = 0; i < S; ++i) hashes[i] = i;
+        std::vector<uint8_t> rows(S * row);
+        file->read_from_disk(hashes, rows.data(), 0, row, row);
+        HbmIndexSearchFile::Pages p;
+        p.term_size = file->term_size();
+        p.canonicalize = file->canonicalize();
+        p.num_hashes = file->num_hashes();
+        p.file_names = file->file_names();
+        p.signature_sizes = { S };
+        p.page_data = { rows.data() };
+        auto mem = std::make_shared<HbmIndexSearchFile>(p);
+        CHECK(mem->counts_size() == file->counts_size() && mem->row_size() == row);
+        ClassicSearch a(file), b(mem);
+        std::vector<SearchResult> ra, rb;
+        a.search(kPyQuery, ra, 0.0, 0);
+        b.search(kPyQuery, rb, 0.0, 0);
+        CHECK(ra.size() == rb.size() && ra.size() == 33);
+        for (size_t i = 0; i < ra.size() && i < rb.size(); ++i)
+            CHECK(std::string(ra[i].doc_name) == rb[i].doc_name && ra[i].score == rb[i].score);
+
+        struct Foreign : IndexSearchFile {
+            std::vector<std::string> names { "x" };
+            void read_from_disk(const std::vector<size_t>&, uint8_t*, size_t, size_t, size_t) override { }
+            uint32_t term_size() const override { return 31; }
+            uint8_t canonicalize() const override { return 1; }
+            uint64_t row_size() const override { return 1; }
+            uint64_t page_size() const override { return 1; }
+            uint64_t num_hashes() const override { return 1; }
+            uint64_t counts_size() const override { return 8; }
+            const std::vector<std::string>& file_names() const override { return names; }
+        };
+        ClassicSearch foreign(std::make_shared<Foreign>());
+        std::vector<SearchResult> r;
+        bool threw = false;
+        try {
+            foreign.search(kPyQuery, r);
+        }
+        catch (const DieException& e) {
+            threw = std::string(e.what()).find("HBM-resident") != std::string::npos;
         }
         CHECK(threw);
     }
