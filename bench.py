@@ -427,6 +427,10 @@ def run_workload(env, wl, primary, parallelism):
     else:
         doc_shards = world
     groups = world // doc_shards
+    # slots per query in a rank's result block: a shard holds 1/doc_shards of a query's documents,
+    # and the all-gather moves the whole padded block, so the block shrinks with the shard (a list
+    # that still outgrew it would be flagged, never cut -- and fail the parity check below)
+    rpq = max(32, rpq // doc_shards)
 
     def open_index(shard_index, shard_count):
         ix = cobs_b200.GpuIndex.procedural(cfg["kind"], cfg["n_docs"], sig, cfg["h"],
