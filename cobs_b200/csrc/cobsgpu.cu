@@ -79,6 +79,9 @@ int guarded(F&& f) {
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;              // owns its allocation
+    DevBuf& operator=(const DevBuf&) = delete;
     void ensure(size_t n) {
         if (n <= cap) return;
         reserve(round_up<size_t>(n + n / 4, 256));
@@ -103,6 +106,9 @@ struct DevBuf {
 struct PinBuf {
     void* p = nullptr;
     size_t cap = 0;
+    PinBuf() = default;
+    PinBuf(const PinBuf&) = delete;              // owns its allocation
+    PinBuf& operator=(const PinBuf&) = delete;
     void ensure(size_t n) {
         if (n <= cap) return;
         reserve(round_up<size_t>(n + n / 4, 256));
@@ -171,13 +177,10 @@ struct U32Buf {
         n = m;
     }
     void clear() { n = 0; }
-    size_t size() const { return n; }
     uint32_t* data() { return p; }
-    const uint32_t* data() const { return p; }
     uint32_t* begin() { return p; }
     uint32_t* end() { return p + n; }
     const uint32_t* begin() const { return p; }
-    const uint32_t* end() const { return p + n; }
     uint32_t& operator[](size_t i) { return p[i]; }
     const uint32_t& operator[](size_t i) const { return p[i]; }
     void push_back(uint32_t v) {
@@ -1819,11 +1822,8 @@ struct cobsgpu_group {
     // needed: cudaMemcpyAsync from pageable memory is staged before it returns
 
     ~cobsgpu_group() {
-        for (auto& g : gs) {
-            if (!devices.empty()) cudaSetDevice(devices[0]);
-            g = GSlot();
-        }
-        for (cobsgpu_index* ix : shards) delete ix;
+        for (cobsgpu_index* ix : shards) delete ix;   // (synchronises the shards' streams)
+        // the slots' merge buffers on the leader are released by their own destructors
     }
 };
 
