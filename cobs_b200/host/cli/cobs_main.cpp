@@ -12,9 +12,11 @@
 #include <cobsgpu.h>
 
 #include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <future>
 #include <iostream>
 #include <map>
 #include <memory>
@@ -44,19 +46,44 @@ struct Batch {
     std::vector<std::string> comments, queries;
 };
 
+// "<comment>\t<count>\n" + "<doc>\t<score>\n" per result, formatted into one buffer per batch
+// and written with a single fwrite (operator<< per field costs more than the GPU search)
+void format_batch(const Batch& b, const std::vector<std::vector<cobs::SearchResult> >& results,
+                  std::string& out) {
+    out.clear();
+    char num[24];
+    auto put_num = [&](unsigned long v) {
+        int n = std::snprintf(num, sizeof(num), "%lu", v);
+        out.append(num, size_t(n));
+    };
+    for (size_t i = 0; i < results.size(); ++i) {
+        out += b.comments[i];
+        out += '\t';
+        put_num(results[i].size());
+        out += '\n';
+        for (const auto& res : results[i]) {
+            out += res.doc_name;
+            out += '\t';
+            put_num(res.score);
+            out += '\n';
+        }
+    }
+}
+
 void flush(cobs::Search& s, Batch& b, double threshold, unsigned num_results) {
     if (b.queries.empty()) return;
     std::vector<std::vector<cobs::SearchResult> > results;
     s.search_batch(b.queries, results, threshold, num_results);
-    for (size_t i = 0; i < results.size(); ++i) {
-        std::cout << b.comments[i] << '\t' << results[i].size() << '\n';
-        for (const auto& res : results[i]) std::cout << res.doc_name << '\t' << res.score << '\n';
-    }
+    std::string out;
+    format_batch(b, results, out);
+    std::cout.write(out.data(), std::streamsize(out.size()));
     b.comments.clear();
     b.queries.clear();
 }
 
-// same record splitting as process_query (src/cobs.cpp:425-462)
+// same record splitting as process_query (src/cobs.cpp:425-462).  The FASTA file is processed as
+// a two-stage pipeline: this thread parses batch i+1 while a worker searches batch i on the GPU,
+// formats its lines and writes them -- in order, so stdout is what the reference prints.
 void process_query(cobs::Search& s, double threshold, unsigned num_results,
                    const std::string& query_line, const std::string& query_file, size_t batch) {
     if (!query_line.empty()) {
@@ -67,11 +94,18 @@ void process_query(cobs::Search& s, double threshold, unsigned num_results,
     else if (!query_file.empty()) {
         std::ifstream qf(query_file);
         std::string line, query, comment;
-        Batch b;
+        Batch parsing, searching;
+        std::future<void> worker;
+        auto dispatch = [&] {
+            if (worker.valid()) worker.get();      // batch i-1 is written before batch i starts
+            std::swap(parsing, searching);
+            worker = std::async(std::launch::async,
+                                [&] { flush(s, searching, threshold, num_results); });
+        };
         auto push = [&] {
-            b.comments.push_back(comment);
-            b.queries.push_back(query);
-            if (b.queries.size() >= batch) flush(s, b, threshold, num_results);
+            parsing.comments.push_back(comment);
+            parsing.queries.push_back(query);
+            if (parsing.queries.size() >= batch) dispatch();
         };
         while (std::getline(qf, line)) {
             if (line.empty()) continue;
@@ -86,11 +120,13 @@ void process_query(cobs::Search& s, double threshold, unsigned num_results,
             }
         }
         if (!query.empty()) push();
-        flush(s, b, threshold, num_results);
+        dispatch();
+        if (worker.valid()) worker.get();
     }
     else {
         cobs::die_with_message("Pass a verbatim query or a query file.");
     }
+    std::cout.flush();
     s.timer().print("search");
 }
 

@@ -62,6 +62,26 @@ HbmIndexSearchFile& hbm(IndexSearchFile& index) {
     return *h;
 }
 
+//! folds the device-side phase times of one call into the reference's Timer keys
+void account_timers(const std::vector<cobsgpu_index*>& shards, Timer& timer) {
+    // shards run concurrently: a phase lasts as long as its slowest shard
+    cobsgpu_timers tm{};
+    for (cobsgpu_index* s : shards) {
+        cobsgpu_timers t{};
+        cobsgpu_get_timers(s, &t);
+        tm.hashes_ms = std::max(tm.hashes_ms, t.hashes_ms);
+        tm.score_ms = std::max(tm.score_ms, t.score_ms);
+        tm.select_ms = std::max(tm.select_ms, t.select_ms);
+        tm.h2d_ms = std::max(tm.h2d_ms, t.h2d_ms);
+        tm.d2h_ms = std::max(tm.d2h_ms, t.d2h_ms);
+    }
+    timer.add("hashes", tm.hashes_ms * 1e-3);
+    timer.add("io", (tm.h2d_ms + tm.d2h_ms) * 1e-3);
+    timer.add("and rows", tm.score_ms * 1e-3);   // gather + AND + add are one fused kernel
+    timer.add("add rows", 0.0);
+    timer.add("sort results", tm.select_ms * 1e-3);
+}
+
 //! runs one packed batch on one index -- a single GPU handle, or a group of document-axis
 //! shards merged on the leader GPU -- and appends (score, file, doc) entries
 void run_index(
@@ -97,22 +117,7 @@ void run_index(
         for (uint64_t e = res.offsets[i]; e < res.offsets[i + 1]; ++e)
             dst.push_back(Entry { res.score[e], file_num, res.doc[e] });
     }
-    // shards run concurrently: a phase lasts as long as its slowest shard
-    cobsgpu_timers tm{};
-    for (cobsgpu_index* s : shards) {
-        cobsgpu_timers t{};
-        cobsgpu_get_timers(s, &t);
-        tm.hashes_ms = std::max(tm.hashes_ms, t.hashes_ms);
-        tm.score_ms = std::max(tm.score_ms, t.score_ms);
-        tm.select_ms = std::max(tm.select_ms, t.select_ms);
-        tm.h2d_ms = std::max(tm.h2d_ms, t.h2d_ms);
-        tm.d2h_ms = std::max(tm.d2h_ms, t.d2h_ms);
-    }
-    timer.add("hashes", tm.hashes_ms * 1e-3);
-    timer.add("io", (tm.h2d_ms + tm.d2h_ms) * 1e-3);
-    timer.add("and rows", tm.score_ms * 1e-3);   // gather + AND + add are one fused kernel
-    timer.add("add rows", 0.0);
-    timer.add("sort results", tm.select_ms * 1e-3);
+    account_timers(shards, timer);
 }
 
 } // namespace
@@ -153,6 +158,37 @@ void ClassicSearch::search_batch(
         for (auto& f : index_files_)
             total_hashes += f->num_hashes() * (queries[i].size() - f->term_size() + 1);
         (total_hashes > 1 ? normal : single_hash).push_back(uint32_t(i));
+    }
+
+    // One index and no single-hash query -- the usual case: the library's lists are the result;
+    // no intermediate entries, no re-packing of the queries.
+    if (index_files_.size() == 1 && single_hash.empty()) {
+        HbmIndexSearchFile& index = hbm(*index_files_[0]);
+        const auto& shards = index.gpu_shards();
+        for (cobsgpu_index* s : shards) {
+            cobsgpu_set_option(s, "timing", 1);
+            cobsgpu_reset_timers(s);
+        }
+        cobsgpu_result res;
+        const int rc = index.gpu_group()
+                       ? cobsgpu_group_search_batch(index.gpu_group(), blob.data(), offsets.data(),
+                                                    uint32_t(nq), threshold, limit, &res)
+                       : cobsgpu_search_batch(shards[0], blob.data(), offsets.data(), uint32_t(nq),
+                                              threshold, limit, &res);
+        if (rc == COBSGPU_ERR_QUERY_TOO_SHORT) exit_error(cobsgpu_last_error());
+        if (rc == COBSGPU_ERR_INVALID_BASE)
+            die_with_message("Invalid DNA base pair in query string. Only ACGT are allowed.");
+        if (rc != COBSGPU_OK) die_with_message(std::string("GPU search failed: ") + cobsgpu_last_error());
+        const std::vector<std::string>& names = index.file_names();
+        for (size_t i = 0; i < nq; ++i) {
+            const uint64_t a = res.offsets[i], b = res.offsets[i + 1];
+            std::vector<SearchResult>& r = results[i];
+            r.resize(b - a);
+            for (uint64_t e = a; e < b; ++e)
+                r[e - a] = SearchResult(names[res.doc[e]].c_str(), res.score[e]);
+        }
+        account_timers(shards, timer_);
+        return;
     }
 
     std::vector<std::vector<Entry> > entries(nq);
