@@ -713,20 +713,22 @@ def run_patterns(env, cfg, sig, index, search, lo, hi, d_batches, off, warmup, s
         n_fpr = 16
         blob, off_f = make_batch(7100, n_fpr, 1030)
         pin = torch.from_numpy(blob).pin_memory().numpy()
-        index.search_packed(pin, off_f, 0.0, 0, raw=True)      # warm-up: buffers reach their size
+        index.search_packed(pin, off_f, 0.0, 0, raw="view")    # warm-up: buffers reach their size
         torch.cuda.synchronize()
         blob, off_f = make_batch(7101, n_fpr, 1030)
         pin = torch.from_numpy(blob).pin_memory().numpy()
         t0 = time.perf_counter()
-        roff, doc, score = index.search_packed(pin, off_f, 0.0, 0, raw=True)
+        # (arrays alias the library's result buffers: what the C++ callers get)
+        roff, doc, score = index.search_packed(pin, off_f, 0.0, 0, raw="view")
         dt = time.perf_counter() - t0
         out["benchmark_fpr_default"] = {
             "threshold": 0.0, "limit": 0, "queries": n_fpr, "kmers_per_query": 1000,
             "value": n_fpr * 1000 / dt, "unit": UNIT, "ms_per_query": 1e3 * dt / n_fpr,
             "results_per_query": int(roff[-1]) // n_fpr,
             "d2h_gbs": (doc.nbytes + score.nbytes) / dt / 1e9,
-            "bound": "result volume: 8 B per document per query sorted on the device and copied "
-                     "over PCIe; K2 itself needs %.2f ms per query at the HBM roofline"
+            "bound": "result volume: 8 B per document per query ordered on the device, copied over "
+                     "PCIe and unpacked into doc/score arrays on the host; K2 itself needs %.2f ms "
+                     "per query at the HBM roofline"
                      % (info.bytes_per_kmer * 1000 / env.peak / 1e6)}
         # one search() per call, the `cobs query <string>` pattern (src/cobs.cpp:417-422)
         blob1, off1 = make_batch(7200, 200)

@@ -228,11 +228,19 @@ class GpuIndex:
 
     @staticmethod
     def _unpack(r, nq, raw):
-        roff = np.ctypeslib.as_array(r.offsets, shape=(nq + 1,)).copy()
+        # raw == "view": no copies -- the arrays alias the library's result buffers and are only
+        # valid until the handle's next calls (see include/cobsgpu.h); for result volumes where
+        # a copy costs more than the search (every document of a large index per query)
+        view = raw == "view"
+        roff = np.ctypeslib.as_array(r.offsets, shape=(nq + 1,))
+        if not view:
+            roff = roff.copy()
         total = int(roff[nq])
         if total:
-            doc = np.ctypeslib.as_array(r.doc, shape=(total,)).copy()
-            score = np.ctypeslib.as_array(r.score, shape=(total,)).copy()
+            doc = np.ctypeslib.as_array(r.doc, shape=(total,))
+            score = np.ctypeslib.as_array(r.score, shape=(total,))
+            if not view:
+                doc, score = doc.copy(), score.copy()
         else:
             doc = np.zeros(0, dtype=np.uint32)
             score = np.zeros(0, dtype=np.uint32)

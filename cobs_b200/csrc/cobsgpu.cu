@@ -1726,6 +1726,15 @@ void collect_batch(cobsgpu_index* ix, Slot& sl) {
         }
     }
     run_exhaustive(ix, sl, redo, sl.limit, &lists, &where, sl.ksplit);
+    if (lists.size() == 1 && redo.size() == nq) {
+        // the whole batch came out of one exhaustive pass, in query order: its CSR is the result
+        // (no second copy of what may be hundreds of megabytes)
+        HostList& L = lists[0];
+        sl.r_off.swap(L.off);
+        sl.r_doc.swap(L.doc);
+        sl.r_score.swap(L.score);
+        return;
+    }
     uint64_t run = 0;
     for (uint32_t i = 0; i < nq; ++i) {
         const HostList& L = lists[where[i].first];
