@@ -1964,7 +1964,11 @@ GSlot& group_submit(cobsgpu_group* grp, const char* queries, const uint64_t* off
         mp.keys[g] = keys;
     }
     const uint64_t all = static_cast<uint64_t>(n) * rpq;
-    gsl.out_stride = static_cast<uint32_t>(limit ? std::min<uint64_t>(limit, all) : all);
+    // merged lists are short in practice: the slots per query are bounded so that a batch's merge
+    // buffers stay within ~256 MB on the leader (a merged list that outgrows them is flagged by
+    // merge_kernel and redone like a candidate overflow, never cut)
+    const uint64_t by_mem = std::max<uint64_t>(rpq, (256ull << 20) / (8ull * std::max<uint32_t>(nq, 1)));
+    gsl.out_stride = static_cast<uint32_t>(limit ? std::min<uint64_t>(limit, all) : std::min<uint64_t>(all, by_mem));
     gsl.d_mkeys.ensure(static_cast<uint64_t>(nq) * gsl.out_stride * 8);
     gsl.d_mcount.ensure(static_cast<size_t>(nq) * 4);
     mp.n_lists = n;

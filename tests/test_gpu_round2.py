@@ -254,3 +254,34 @@ def test_few_long_queries_take_the_k_split_kernel(kind, n_docs, sig, h, ps):
             for q, r in zip(qs, g.search_batch(qs, thr, k)):
                 assert as_list(r) == oracle.search(o, q, thr, k), (lens, thr, k)
     g.close()
+
+
+def test_merge_flags_lists_longer_than_the_output_stride():
+    """the shard merge never cuts a list silently either: a merged list that does not fit the
+    caller's out_per_query is flagged COUNT_OVERFLOW (unless a limit bounds it)"""
+    torch = pytest.importorskip("torch")
+    nq, rpq, n_lists = 3, 8, 2
+    counts = torch.tensor([[3, 8, 0], [2, 8, 1]], dtype=torch.int32, device="cuda")
+    hk = np.zeros((n_lists, nq, rpq), dtype=np.uint64)
+    hc = counts.cpu().numpy()
+    for l in range(n_lists):
+        for q in range(nq):
+            for i in range(int(hc[l, q])):
+                score, doc = 50 - i, 1000 * l + 10 * q + i
+                hk[l, q, i] = ((~score & 0xFFFFFFFF) << 32) | doc
+    keys = torch.from_numpy(hk.view(np.int64)).cuda()
+    out_counts = torch.zeros(nq, dtype=torch.int32, device="cuda")
+    out_keys = torch.zeros((nq, 8), dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    cobs_b200.merge_device(0, n_lists, nq, rpq, counts.data_ptr(), keys.data_ptr(), 0, 8,
+                           out_counts.data_ptr(), out_keys.data_ptr(), st)
+    torch.cuda.synchronize()
+    c = out_counts.cpu().numpy().view(np.uint32)
+    assert c.tolist() == [5, 0xFFFFFFFF, 1]          # 16 merged results do not fit 8 slots
+    d, s_ = cobs_b200.decode_keys(out_keys[0, :5].cpu().numpy().view(np.uint64))
+    assert s_.tolist() == [50, 50, 49, 49, 48] and d.tolist() == [0, 1000, 1, 1001, 2]
+    # with a limit of 4 every list fits
+    cobs_b200.merge_device(0, n_lists, nq, rpq, counts.data_ptr(), keys.data_ptr(), 4, 8,
+                           out_counts.data_ptr(), out_keys.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert out_counts.cpu().numpy().view(np.uint32).tolist() == [4, 4, 1]
