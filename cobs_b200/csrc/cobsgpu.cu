@@ -234,6 +234,7 @@ struct Slot {
     size_t meta_qoff = 0, meta_koff = 0, meta_thr = 0, meta_bad = 0;
     size_t out_off = 0, out_cc = 0, out_keys = 0;
     const char* dev_queries = nullptr;
+    uint32_t* small_cc = nullptr;        // small batches: zeroed candidate counters inside d_meta
     PinBuf h_meta, h_out;
     cudaEvent_t ev_meta = nullptr, ev_in = nullptr, ev_main = nullptr, ev_out = nullptr;
     // the submitted batch
@@ -941,7 +942,7 @@ static constexpr uint32_t TOPK_MAX_K = 1024;      // largest -l served by the pe
 // queries (unless they already live on the device) and of the metadata block, K1 -- all on `st`.
 void prepare_batch(cobsgpu_index* ix, Slot& sl, const char* queries, bool dev_queries,
                    const uint64_t* offsets, uint32_t q0, uint32_t q1, double threshold,
-                   cudaStream_t st) {
+                   cudaStream_t st, bool pack_small = false) {
     const uint32_t nq = q1 - q0;
     const uint32_t k = ix->term_size;
     if (std::isnan(threshold)) throw Err{ COBSGPU_ERR_INVALID_ARG, "threshold is NaN" };
@@ -1001,7 +1002,36 @@ void prepare_batch(cobsgpu_index* ix, Slot& sl, const char* queries, bool dev_qu
     const uint64_t kmers = sl.total_kmers;
     const uint64_t blob_bytes = sl.qoff[nq];
 
-    {
+    sl.small_cc = nullptr;
+    if (pack_small && !dev_queries) {
+        // A handful of queries: ONE upload carries everything -- flags | bad | qoff | koff | thr |
+        // zeroed candidate counters | the query bytes -- instead of a copy, a second copy and a
+        // memset, each of which costs a few microseconds of pure latency.
+        PhaseScope ps(ix, PH_H2D, st);
+        const size_t nq1 = std::max<size_t>(nq, 1);
+        sl.meta_bad = 8;
+        sl.meta_qoff = round_up<size_t>(sl.meta_bad + nq1 * 4, 8);
+        sl.meta_koff = sl.meta_qoff + (static_cast<size_t>(nq) + 1) * 8;
+        sl.meta_thr = sl.meta_koff + round_up<size_t>((static_cast<size_t>(nq) + 1) * 4, 8);
+        const size_t meta_cc = round_up<size_t>(sl.meta_thr + nq1 * 4, 8);
+        const size_t meta_q = round_up<size_t>(meta_cc + nq1 * 4, 16);
+        const size_t total = meta_q + blob_bytes;
+        sl.d_meta.ensure(total + 16);
+        if (sl.ev_meta) CK(cudaEventSynchronize(sl.ev_meta));   // previous upload out of h_meta done
+        sl.h_meta.ensure(total);
+        char* hm = sl.h_meta.as<char>();
+        std::memset(hm, 0x7F, sl.meta_bad + nq1 * 4);
+        std::memcpy(hm + sl.meta_qoff, sl.qoff.data(), (static_cast<size_t>(nq) + 1) * 8);
+        std::memcpy(hm + sl.meta_koff, sl.koff.data(), (static_cast<size_t>(nq) + 1) * 4);
+        if (nq) std::memcpy(hm + sl.meta_thr, sl.thr.data(), static_cast<size_t>(nq) * 4);
+        std::memset(hm + meta_cc, 0, nq1 * 4);
+        std::memcpy(hm + meta_q, queries + base, blob_bytes);
+        CK(cudaMemcpyAsync(sl.d_meta.p, hm, total, cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(sl.ev(sl.ev_meta), st));
+        sl.meta_resident = false;   // (the block layout differs from the cached one)
+        sl.dev_queries = sl.d_meta.as<char>() + meta_q;
+        sl.small_cc = reinterpret_cast<uint32_t*>(sl.d_meta.as<char>() + meta_cc);
+    } else {
         PhaseScope ps(ix, PH_H2D, st);
         if (dev_queries) {
             sl.dev_queries = queries + base;
@@ -1109,7 +1139,7 @@ struct PassPlan {
 void launch_select(cobsgpu_index* ix, const Slot& src, Slot& work, const uint32_t* d_qlist,
                    uint32_t n_slots, const PassPlan& pl, uint32_t max_T, uint32_t* cand_count,
                    uint64_t* out_keys, uint32_t* out_counts, uint32_t stride, bool report_bad,
-                   cudaStream_t st, bool fuse_csr = false) {
+                   cudaStream_t st, bool fuse_csr = false, char* host_out = nullptr) {
     PhaseScope ps(ix, PH_SELECT, st);
     const uint32_t cap = pl.cap;
     uint64_t* cand = work.d_cand.as<uint64_t>();
@@ -1155,6 +1185,13 @@ void launch_select(cobsgpu_index* ix, const Slot& src, Slot& work, const uint32_
         fp.csr_keys = work.o_keys();
         fp.flags_src = src.d_flags();
         fp.flags_dst = work.o_flags();
+        if (host_out) {
+            // ... straight into the (device-mapped) pinned result buffer: no copy afterwards
+            fp.csr_off = reinterpret_cast<uint64_t*>(host_out + work.out_off);
+            fp.csr_keys = reinterpret_cast<uint64_t*>(host_out + work.out_keys);
+            fp.flags_dst = reinterpret_cast<int*>(host_out);
+            fp.cc_dst = reinterpret_cast<uint32_t*>(host_out + work.out_cc);
+        }
     }
     const size_t smem = static_cast<size_t>(fp.fin_sort_max) * 8;
     static bool attr_set[64] = {};
@@ -1171,10 +1208,11 @@ void launch_select(cobsgpu_index* ix, const Slot& src, Slot& work, const uint32_
 // K2 of one pass over `n_slots` queries of the batch in `src` (slot i = batch query qlist[i],
 // or i when d_qlist is null): fills work.d_cand / cand_count (zeroed here).
 void launch_pass_score(cobsgpu_index* ix, const Slot& src, Slot& work, const uint32_t* d_qlist,
-                       uint32_t n_slots, const PassPlan& pl, uint32_t* cand_count, cudaStream_t st) {
+                       uint32_t n_slots, const PassPlan& pl, uint32_t* cand_count, cudaStream_t st,
+                       bool counters_zeroed = false) {
     const uint32_t cap = pl.cap;
     work.d_cand.ensure(static_cast<uint64_t>(n_slots) * cap * 8);
-    CK(cudaMemsetAsync(cand_count, 0, static_cast<size_t>(n_slots) * 4, st));
+    if (!counters_zeroed) CK(cudaMemsetAsync(cand_count, 0, static_cast<size_t>(n_slots) * 4, st));
     ScoreParams sp = base_params(ix, src, d_qlist, n_slots);
     sp.cand_count = cand_count;
     sp.cand = work.d_cand.as<uint64_t>();
@@ -1573,7 +1611,7 @@ Slot& submit_batch(cobsgpu_index* ix, const char* queries, const uint64_t* offse
     const bool small = nq <= FIN_WARPS;
     cudaStream_t st_in = small ? ix->stream : ix->s_in;
     cudaStream_t st_out = small ? ix->stream : ix->s_out;
-    prepare_batch(ix, sl, queries, false, offsets, q0, q1, threshold, st_in);
+    prepare_batch(ix, sl, queries, false, offsets, q0, q1, threshold, st_in, small);
     if (!small) CK(cudaEventRecord(sl.ev(sl.ev_in), st_in));
     sl.q0 = q0;
     sl.threshold = threshold;
@@ -1636,14 +1674,28 @@ Slot& submit_batch(cobsgpu_index* ix, const char* queries, const uint64_t* offse
     const size_t ob = out_bytes(sl, n_main, pl);
     sl.d_out.ensure(ob);
     sl.d_res_count.ensure(static_cast<size_t>(n_main) * 4);
-    launch_pass_score(ix, sl, sl, d_ql, n_main, pl, sl.o_cc(), st);
     const bool fuse_csr = small && sl.huge_ids.empty();
+    const uint64_t max_keys = (ob - sl.out_keys) / 8;
+    if (fuse_csr && sl.small_cc && ob <= (64u << 20)) {
+        // Zero-copy result: K3 writes offsets, counts, flags and keys straight into the pinned
+        // host buffer (device-mapped), so the batch is upload -> K1 -> K2 -> K3 and nothing else.
+        sl.h_out.ensure(ob);
+        char* mapped = nullptr;
+        CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&mapped), sl.h_out.p, 0));
+        launch_pass_score(ix, sl, sl, d_ql, n_main, pl, sl.small_cc, st, true);
+        launch_select(ix, sl, sl, d_ql, n_main, pl, main_max_T, sl.small_cc, sl.d_cand.as<uint64_t>(),
+                      sl.d_res_count.as<uint32_t>(), pl.cap, false, st, true, mapped);
+        sl.spec_keys = max_keys;
+        CK(cudaEventRecord(sl.ev(sl.ev_out), st));
+        commit.ok = true;
+        return sl;
+    }
+    launch_pass_score(ix, sl, sl, d_ql, n_main, pl, sl.o_cc(), st);
     launch_select(ix, sl, sl, d_ql, n_main, pl, main_max_T, sl.o_cc(), sl.d_cand.as<uint64_t>(),
                   sl.d_res_count.as<uint32_t>(), pl.cap, false, st, fuse_csr);
     if (!fuse_csr) launch_csr(ix, sl, sl, n_main, pl.cap, st);
     if (!small) CK(cudaEventRecord(sl.ev(sl.ev_main), st));
     // ONE device-to-host copy in the common case: the header and the first spec_keys keys
-    const uint64_t max_keys = (ob - sl.out_keys) / 8;
     // (sized from what the previous batch returned, with headroom)
     sl.spec_keys = std::min<uint64_t>(
         max_keys, std::max<uint64_t>(std::max<uint64_t>(8192, 8ull * n_main), ix->spec_hint + ix->spec_hint / 4));

@@ -256,6 +256,8 @@ struct FinalizeParams {
     uint64_t* csr_keys;
     const int* flags_src;
     int* flags_dst;
+    uint32_t* cc_dst;          // optional: copy of cand_count next to the offsets (the targets may
+                               // be device-mapped HOST memory: no copy engine involved at all)
 };
 
 __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(FinalizeParams p) {
@@ -351,6 +353,8 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(FinalizeParams
             for (uint32_t i = 0; i <= p.nq; ++i) p.csr_off[i] = off_s[i];
             p.flags_dst[0] = p.flags_src[0];
             p.flags_dst[1] = p.flags_src[1];
+            if (p.cc_dst)
+                for (uint32_t i = 0; i < p.nq; ++i) p.cc_dst[i] = p.cand_count[i];
         }
         __syncthreads();
         if (q < p.nq) {
