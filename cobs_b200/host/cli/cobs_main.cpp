@@ -11,6 +11,7 @@
 
 #include <cobsgpu.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -18,6 +19,7 @@
 #include <fstream>
 #include <future>
 #include <iostream>
+#include <iterator>
 #include <map>
 #include <memory>
 #include <random>
@@ -278,14 +280,137 @@ int benchmark_fpr(int argc, char** argv) {
     return 0;
 }
 
+// `cobs classic-construct <input> <out_file>`: the reference's subtool (src/cobs.cpp:117-190) for
+// FASTA and plain-text documents, built on the device (cobsgpu_construct_classic) and written in
+// the reference's file format -- byte-identical to what the reference writes from the same files.
+// One document per file, named after the file without its extension, ordered by path.
+int classic_construct(int argc, char** argv) {
+    std::string input, out_file;
+    unsigned num_hashes = 1, term_size = 31;
+    double fpr = 0.3;
+    bool no_canonicalize = false, clobber = false;
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        auto value = [&](const char* name) -> std::string {
+            if (i + 1 >= argc) {
+                std::cerr << "Error: option " << name << " requires an argument!\n";
+                std::exit(-1);
+            }
+            return argv[++i];
+        };
+        if (a == "-h" || a == "--num-hashes") num_hashes = unsigned(std::strtoul(value("-h").c_str(), nullptr, 10));
+        else if (a == "-f" || a == "--false-positive-rate") fpr = std::atof(value("-f").c_str());
+        else if (a == "-k" || a == "--term-size") term_size = unsigned(std::strtoul(value("-k").c_str(), nullptr, 10));
+        else if (a == "--no-canonicalize") no_canonicalize = true;
+        else if (a == "-C" || a == "--clobber") clobber = true;
+        else if (a == "--device") cobs::gopt_gpu_device = std::atoi(value("--device").c_str());
+        else if (a == "-T" || a == "--threads" || a == "-m" || a == "--memory" || a == "--tmp-path" ||
+                 a == "--file-type") value(a.c_str());      // accepted for compatibility
+        else if (a == "--continue" || a == "--keep-temporary") { }
+        else if (!a.empty() && a[0] == '-') {
+            std::cerr << "Error: unknown option \"" << a << "\".\n";
+            return -1;
+        }
+        else if (input.empty()) input = a;
+        else if (out_file.empty()) out_file = a;
+    }
+    if (input.empty() || out_file.empty()) {
+        std::cerr << "Usage: cobs classic-construct [-h num_hashes] [-f fpr] [-k term_size] "
+                     "[--no-canonicalize] [-C] <input dir or file> <out_file>\n";
+        return -1;
+    }
+    namespace fs = cobs::fs;
+    if (fs::exists(out_file) && !clobber)
+        cobs::die_with_message("Output file exists, will not overwrite without --clobber.");
+    auto is_fasta = [](const std::string& ext) {
+        for (const char* e : { ".fa", ".fasta", ".fna", ".ffn", ".faa", ".frn" })
+            if (ext == e) return true;
+        return false;
+    };
+    std::vector<fs::path> files;
+    auto consider = [&](const fs::path& p) {
+        const std::string ext = p.extension().string();
+        if (is_fasta(ext) || ext == ".txt") files.push_back(p);
+    };
+    if (fs::is_directory(input)) {
+        for (auto& e : fs::recursive_directory_iterator(input))
+            if (e.is_regular_file()) consider(e.path());
+    }
+    else consider(input);
+    std::sort(files.begin(), files.end());
+    if (files.empty()) cobs::die_with_message("No FASTA or text documents found in \"" + input + "\"");
+
+    // documents -> sequences (records of a FASTA file the way the reference walks it,
+    // cobs/fasta_file.hpp:156-182: '>' / ';' lines and empty lines end a record)
+    std::vector<std::string> names;
+    std::string sequences;
+    std::vector<uint64_t> seq_offsets { 0 };
+    std::vector<uint32_t> seq_doc;
+    for (size_t d = 0; d < files.size(); ++d) {
+        names.push_back(files[d].stem().string());
+        std::ifstream in(files[d], std::ios::binary);
+        std::string data((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+        auto end_record = [&] {
+            if (sequences.size() > seq_offsets.back()) {
+                seq_offsets.push_back(sequences.size());
+                seq_doc.push_back(uint32_t(d));
+            }
+        };
+        if (!is_fasta(files[d].extension().string())) {
+            sequences += data;
+            end_record();
+            continue;
+        }
+        size_t pos = 0;
+        while (pos <= data.size()) {
+            size_t nl = data.find('\n', pos);
+            if (nl == std::string::npos) nl = data.size();
+            if (nl == pos || data[pos] == '>' || data[pos] == ';') end_record();
+            else sequences.append(data, pos, nl - pos);
+            pos = nl + 1;
+        }
+        end_record();
+    }
+    std::vector<const char*> name_ptrs;
+    for (auto& n : names) name_ptrs.push_back(n.c_str());
+    cobsgpu_construct_desc desc;
+    std::memset(&desc, 0, sizeof(desc));
+    desc.struct_size = sizeof(desc);
+    desc.term_size = term_size;
+    desc.canonicalize = no_canonicalize ? 0 : 1;
+    desc.num_hashes = num_hashes;
+    desc.signature_size = 0;
+    desc.false_positive_rate = fpr;
+    desc.n_docs = uint32_t(names.size());
+    desc.n_seqs = uint32_t(seq_doc.size());
+    desc.doc_names = name_ptrs.data();
+    desc.sequences = sequences.data();
+    desc.seq_offsets = seq_offsets.data();
+    desc.seq_doc = seq_doc.data();
+    desc.device = cobs::gopt_gpu_device;
+    cobsgpu_index* ix = nullptr;
+    if (cobsgpu_construct_classic(&desc, &ix) != COBSGPU_OK)
+        cobs::die_with_message(std::string("construction failed: ") + cobsgpu_last_error());
+    const int rc = cobsgpu_index_save(ix, out_file.c_str());
+    cobsgpu_index_info info;
+    cobsgpu_index_get_info(ix, &info);
+    std::cerr << "classic index: " << info.n_docs << " documents, signature size "
+              << cobsgpu_index_signature_size(ix, 0) << ", " << info.num_hashes << " hashes -> "
+              << out_file << std::endl;
+    cobsgpu_index_close(ix);
+    if (rc != COBSGPU_OK) cobs::die_with_message(std::string("could not write index: ") + cobsgpu_last_error());
+    return 0;
+}
+
 void usage(const char* prog) {
     std::cout << "(Co)mpact (B)it-Sliced (S)ignature Index for Genome Search -- B200 query path\n\n"
               << "Usage: " << prog << " <subtool> ...\n\n"
               << "Available subtools:\n"
               << "  query          query an index (classic or compact) on the GPU\n"
               << "  benchmark-fpr  the reference's query micro-benchmark (classic index)\n"
+              << "  classic-construct  build a classic index from FASTA / text documents on the GPU\n"
               << "  version        print version\n\n"
-              << "Index construction and the other subtools of the reference are not part of\n"
+              << "Compact construction and the other subtools of the reference are not part of\n"
               << "this build; indices written by the reference are read as they are.\n";
 }
 
@@ -300,6 +425,7 @@ int main(int argc, char** argv) {
     try {
         if (tool == "query") return query(argc - 1, argv + 1);
         if (tool == "benchmark-fpr") return benchmark_fpr(argc - 1, argv + 1);
+        if (tool == "classic-construct") return classic_construct(argc - 1, argv + 1);
         if (tool == "version") {
             std::cout << "COBS B200 query path, C ABI version " << cobsgpu_version() << std::endl;
             return 0;

@@ -83,3 +83,31 @@ def test_construct_then_query_roundtrip_properties():
             assert i in doc.tolist()                    # threshold 1.0: all k-mers present
     # identical to the oracle's view of the saved file
     g.close()
+
+
+def test_cli_classic_construct_is_byte_identical(golden, tmp_path):
+    """`cobs classic-construct <dir> <out>` (the reference's subtool, src/cobs.cpp:117-190) on the
+    committed FASTA fixtures writes the very bytes the reference wrote"""
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "build", "cobs")
+    docs = os.path.join(GOLDEN_DIR, "construct_docs")
+    for c in golden["construct"]:
+        out = str(tmp_path / c["file"])
+        cmd = [exe, "classic-construct", docs, out, "-h", str(c["num_hashes"]),
+               "-f", repr(c["false_positive_rate"])]
+        if not c["canonicalize"]:
+            cmd.append("--no-canonicalize")
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr
+        assert open(out, "rb").read() == open(golden_path(c["file"]), "rb").read(), c["file"]
+        # refuses to overwrite without -C, like the reference
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+        assert r.returncode != 0 and "will not overwrite" in r.stderr
+        r = subprocess.run(cmd + ["-C"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr
+    # and the result answers queries through the same CLI
+    seq = "".join(l.strip() for l in open(os.path.join(docs, "beta.fasta")) if not l.startswith(">"))
+    r = subprocess.run([exe, "query", "-i", out, "-t", "0.9", seq[40:140]], stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout == "beta\t70\n", r.stdout + r.stderr
