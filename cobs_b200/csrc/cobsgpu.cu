@@ -150,11 +150,21 @@ struct PinBuf {
 struct U32Buf {
     uint32_t* p = nullptr;
     size_t n = 0, cap = 0;
+    bool owned = true;   // false: a view of pinned memory that a slot owns (see alias())
     U32Buf() = default;
     U32Buf(const U32Buf&) = delete;
-    U32Buf(U32Buf&& o) noexcept : p(o.p), n(o.n), cap(o.cap) {
+    U32Buf(U32Buf&& o) noexcept : p(o.p), n(o.n), cap(o.cap), owned(o.owned) {
         o.p = nullptr;
         o.n = o.cap = 0;
+        o.owned = true;
+    }
+    // view of `m` elements at `ptr` (not owned, never freed or grown in place)
+    void alias(uint32_t* ptr, size_t m) {
+        if (owned) std::free(p);
+        p = ptr;
+        n = m;
+        cap = 0;
+        owned = false;
     }
     U32Buf& operator=(const U32Buf& o) {
         if (this != &o) {
@@ -163,20 +173,37 @@ struct U32Buf {
         }
         return *this;
     }
-    ~U32Buf() { std::free(p); }
+    ~U32Buf() {
+        if (owned) std::free(p);
+    }
     void reserve(size_t m) {
-        if (m <= cap) return;
-        m = std::max(m, cap + cap / 2);
-        void* q = std::realloc(p, m * 4);
-        if (!q) throw std::bad_alloc();
-        p = static_cast<uint32_t*>(q);
-        cap = m;
+        if (owned && m <= cap) return;
+        const size_t want = owned ? std::max(m, cap + cap / 2) : std::max(m, n);
+        if (want > (static_cast<size_t>(1) << 60)) throw std::bad_alloc();
+        if (owned) {
+            void* q = std::realloc(p, want * 4);
+            if (!q) throw std::bad_alloc();
+            p = static_cast<uint32_t*>(q);
+        } else {   // leaving the view: own a copy of what it showed
+            void* q = std::malloc(std::max<size_t>(want, 1) * 4);
+            if (!q) throw std::bad_alloc();
+            if (n) std::memcpy(q, p, n * 4);
+            p = static_cast<uint32_t*>(q);
+            owned = true;
+        }
+        cap = want;
     }
     void resize(size_t m) {   // new elements are NOT initialised
         reserve(m);
         n = m;
     }
-    void clear() { n = 0; }
+    void clear() {
+        if (!owned) {
+            p = nullptr;
+            owned = true;
+        }
+        n = 0;
+    }
     uint32_t* data() { return p; }
     uint32_t* begin() { return p; }
     uint32_t* end() { return p + n; }
@@ -198,6 +225,7 @@ struct U32Buf {
         std::swap(p, o.p);
         std::swap(n, o.n);
         std::swap(cap, o.cap);
+        std::swap(owned, o.owned);
     }
 };
 
@@ -236,6 +264,7 @@ struct Slot {
     const char* dev_queries = nullptr;
     uint32_t* small_cc = nullptr;        // small batches: zeroed candidate counters inside d_meta
     PinBuf h_meta, h_out;
+    PinBuf h_res;                        // exhaustive results land here and are handed out as they are
     cudaEvent_t ev_meta = nullptr, ev_in = nullptr, ev_main = nullptr, ev_out = nullptr;
     // the submitted batch
     bool busy = false;
@@ -1317,6 +1346,8 @@ const uint32_t* upload_qlist(Slot& work, const std::vector<uint32_t>& ids, size_
 uint32_t exhaustive_dense(cobsgpu_index* ix, const Slot& src, Slot& work, const uint32_t* d_ql,
                           uint32_t n, uint32_t max_T, uint64_t limit, bool ksplit, int stage,
                           cudaStream_t st) {
+    // (the counting sort writes documents[] and scores[] as two u32 arrays -- what the C ABI
+    // hands out -- where the candidate paths write 64-bit keys; see run_exhaustive)
     // k-split: the k-mers of every query are cut into chunks that become work items of their own
     // (partial counts added into the u16 vector), sized so that the items fill the GPU
     uint32_t kchunk = 0, n_kchunks = 1;
@@ -1412,6 +1443,8 @@ uint32_t exhaustive_dense(cobsgpu_index* ix, const Slot& src, Slot& work, const 
     dp.n_chunks = n_chunks;
     dp.hist = work.d_hist.as<uint32_t>();
     dp.limit = limit;
+    dp.n_slots = n;
+    dp.soa = 1;
     const dim3 grid(n_chunks, n);
     auto final_pass = [&](uint32_t* totals) {
         // slot totals -> CSR offsets -> scatter into the result area
@@ -1455,7 +1488,8 @@ uint32_t exhaustive_dense(cobsgpu_index* ix, const Slot& src, Slot& work, const 
 // limit, for queries whose candidates overflowed the fused path, and for queries beyond 16 planes.
 void run_exhaustive(cobsgpu_index* ix, const Slot& src, const std::vector<uint32_t>& ids,
                     uint64_t limit, std::vector<HostList>* lists,
-                    std::vector<std::pair<uint32_t, uint32_t>>* where, bool ksplit = false) {
+                    std::vector<std::pair<uint32_t, uint32_t>>* where, bool ksplit = false,
+                    PinBuf* res_pin = nullptr) {
     if (ids.empty()) return;
     cudaStream_t st = ix->stream;
     Slot& work = ix->aux;
@@ -1491,8 +1525,10 @@ void run_exhaustive(cobsgpu_index* ix, const Slot& src, const std::vector<uint32
             pl.mode = MODE_DENSE32;
             work.d_out.ensure(out_bytes(work, n, pl));
             uint32_t cand_cap = 0;
+            bool soa = false;   // result area holds doc[] | score[] instead of keys
             if (!huge) {
                 cand_cap = exhaustive_dense(ix, src, work, d_ql, n, max_T, limit, ksplit, 0, st);
+                soa = cand_cap == 0;
             } else {
                 work.d_res_count.ensure(static_cast<size_t>(n) * 4);
                 launch_pass_score(ix, src, work, d_ql, n, pl, work.o_cc(), st);
@@ -1515,6 +1551,7 @@ void run_exhaustive(cobsgpu_index* ix, const Slot& src, const std::vector<uint32
                 for (uint32_t i = 0; i < n; ++i) over = over || cc[i] > cand_cap;
                 if (over) {
                     exhaustive_dense(ix, src, work, d_ql, n, max_T, limit, ksplit, 1, st);
+                    soa = true;
                     CK(cudaMemcpyAsync(work.h_out.p, work.d_out.p, work.out_keys, cudaMemcpyDeviceToHost, st));
                     CK(cudaStreamSynchronize(st));
                 }
@@ -1524,9 +1561,22 @@ void run_exhaustive(cobsgpu_index* ix, const Slot& src, const std::vector<uint32
             const uint64_t* off = reinterpret_cast<const uint64_t*>(work.h_out.as<char>() + work.out_off);
             L.off.assign(off, off + n + 1);
             const uint64_t total = L.off[n];
-            L.doc.resize(total);
-            L.score.resize(total);
-            if (total) {
+            // One pass that covers the whole batch and came out as doc[] | score[]: the arrays land
+            // in the batch slot's own pinned buffer and are handed out as they are -- for lists of
+            // every document of a large index, unpacking and copying cost more than the search.
+            const bool hand_out = soa && res_pin != nullptr && sub >= list.size() && list.size() == ids.size();
+            if (hand_out && total) {
+                res_pin->ensure(total * 8);
+                {
+                    PhaseScope ps(ix, PH_D2H, st);
+                    CK(cudaMemcpyAsync(res_pin->p, work.o_keys(), total * 8, cudaMemcpyDeviceToHost, st));
+                }
+                CK(cudaStreamSynchronize(st));
+                L.doc.alias(res_pin->as<uint32_t>(), total);
+                L.score.alias(res_pin->as<uint32_t>() + total, total);
+            } else if (total) {
+                L.doc.resize(total);
+                L.score.resize(total);
                 work.h_out.ensure(work.out_keys + total * 8);
                 {
                     PhaseScope ps(ix, PH_D2H, st);
@@ -1534,8 +1584,13 @@ void run_exhaustive(cobsgpu_index* ix, const Slot& src, const std::vector<uint32
                                        cudaMemcpyDeviceToHost, st));
                 }
                 CK(cudaStreamSynchronize(st));
-                decode_keys(reinterpret_cast<const uint64_t*>(work.h_out.as<char>() + work.out_keys), total,
-                            L.doc.data(), L.score.data());
+                const char* got = work.h_out.as<char>() + work.out_keys;
+                if (soa) {
+                    std::memcpy(L.doc.data(), got, total * 4);
+                    std::memcpy(L.score.data(), got + total * 4, total * 4);
+                } else {
+                    decode_keys(reinterpret_cast<const uint64_t*>(got), total, L.doc.data(), L.score.data());
+                }
             }
             for (size_t i = 0; i < n; ++i)
                 (*where)[list[b + i]] = { static_cast<uint32_t>(lists->size() - 1), static_cast<uint32_t>(i) };
@@ -1777,7 +1832,8 @@ void collect_batch(cobsgpu_index* ix, Slot& sl) {
             return;
         }
     }
-    run_exhaustive(ix, sl, redo, sl.limit, &lists, &where, sl.ksplit);
+    run_exhaustive(ix, sl, redo, sl.limit, &lists, &where, sl.ksplit,
+                   redo.size() == nq ? &sl.h_res : nullptr);
     if (lists.size() == 1 && redo.size() == nq) {
         // the whole batch came out of one exhaustive pass, in query order: its CSR is the result
         // (no second copy of what may be hundreds of megabytes)

@@ -40,9 +40,13 @@ struct DenseSortParams {
     uint32_t* hist;             // [n_slots][n_chunks][256]; after the scan: start offsets
     uint32_t* slot_total;       // [n_slots] entries kept (cut at `limit` in the last pass)
     uint64_t limit;             // last pass only, 0 = all
-    // destination: pass 1 -> keys_out[slot * cap ...]; pass 0 / 2 -> keys_out[csr_off[slot] ...]
+    // destination: pass 1 -> keys_out[slot * cap ...]; pass 0 / 2 -> keys_out[csr_off[slot] ...],
+    // or, with soa != 0, two u32 arrays in the same place: documents [total], then scores [total]
+    // (total = csr_off[n_slots]) -- the form the C ABI hands out, so the host copies nothing
     uint64_t* keys_out;
     const uint64_t* csr_off;
+    uint32_t n_slots;
+    uint32_t soa;
     int pass;                   // 0: one byte, final; 1: low byte of 16-bit counts; 2: high byte, final
 };
 
@@ -142,6 +146,9 @@ __global__ void __launch_bounds__(DS_THREADS) ds_scatter_kernel(DenseSortParams 
     bin_off[threadIdx.x] = p.hist[(static_cast<uint64_t>(slot) * p.n_chunks + chunk) * 256 + threadIdx.x];
     uint64_t* out = p.pass == 1 ? p.keys_out + static_cast<uint64_t>(slot) * p.cap
                                 : p.keys_out + p.csr_off[slot];
+    const bool soa = p.pass != 1 && p.soa != 0;
+    uint32_t* out_doc = reinterpret_cast<uint32_t*>(p.keys_out) + (soa ? p.csr_off[slot] : 0);
+    uint32_t* out_score = out_doc + (soa ? p.csr_off[p.n_slots] : 0);
     const uint64_t limit = (p.pass != 1 && p.limit != 0) ? p.limit : ~0ull;
     for (uint32_t r = 0; r < DS_CHUNK / DS_THREADS; ++r) {
         for (uint32_t i = threadIdx.x; i < (DS_THREADS / 32) * 256; i += DS_THREADS) (&warp_cnt[0][0])[i] = 0;
@@ -170,7 +177,14 @@ __global__ void __launch_bounds__(DS_THREADS) ds_scatter_kernel(DenseSortParams 
         __syncthreads();
         if (keep) {
             const uint64_t pos = static_cast<uint64_t>(warp_cnt[warp][bin]) + rank;
-            if (pos < limit) out[pos] = key;
+            if (pos < limit) {
+                if (soa) {
+                    out_doc[pos] = key_doc(key);
+                    out_score[pos] = key_score(key);
+                } else {
+                    out[pos] = key;
+                }
+            }
         }
         __syncthreads();
     }
