@@ -259,6 +259,8 @@ struct Slot {
     // d_out = [flags 2 x int | offsets (nq+1) x u64 | cand_count nq x u32 | keys ...]
     DevBuf d_queries, d_meta, d_hashes, d_cand, d_scratch, d_res_count, d_out, d_qlist, d_dense;
     DevBuf d_hist, d_total;              // counting sort of the exhaustive lists (aux slot only)
+    DevBuf d_out_alt;                    // second result area of the pipelined exhaustive passes
+    cudaEvent_t ev_pipe[4] = { nullptr, nullptr, nullptr, nullptr };   // [done 0/1, copied 0/1]
     size_t meta_qoff = 0, meta_koff = 0, meta_thr = 0, meta_bad = 0;
     size_t out_off = 0, out_cc = 0, out_keys = 0;
     const char* dev_queries = nullptr;
@@ -327,7 +329,8 @@ struct Slot {
         h_out.reserve(o.h_out.cap);
     }
     void release() {
-        for (cudaEvent_t* e : { &ev_meta, &ev_in, &ev_main, &ev_out })
+        for (cudaEvent_t* e : { &ev_meta, &ev_in, &ev_main, &ev_out, &ev_pipe[0], &ev_pipe[1], &ev_pipe[2],
+                                &ev_pipe[3] })
             if (*e) {
                 cudaEventDestroy(*e);
                 *e = nullptr;
@@ -379,6 +382,7 @@ struct cobsgpu_index {
     uint32_t max_candidates = 1024;
     uint32_t max_batch = 16384;
     uint64_t workspace_bytes = 1024ull << 20;
+    uint64_t pipe_bytes = 32ull << 20;    // result bytes per copy of the pipelined exhaustive passes
     bool timing = false;
 
     // execution state: three streams so that consecutive batches overlap -- s_in uploads the
@@ -1450,7 +1454,7 @@ uint32_t exhaustive_dense(cobsgpu_index* ix, const Slot& src, Slot& work, const 
         // slot totals -> CSR offsets -> scatter into the result area
         dp.slot_total = totals;
         ds_hist_kernel<<<grid, DS_THREADS, 0, st>>>(dp);
-        ds_scan_kernel<<<n, 256, 0, st>>>(dp);
+        ds_scan_kernel<<<n, 256 * DS_SCAN_GROUPS, 0, st>>>(dp);
         scan_offsets_kernel<<<1, 1024, 0, st>>>(totals, n, work.o_off());
         dp.keys_out = work.o_keys();
         dp.csr_off = work.o_off();
@@ -1469,7 +1473,7 @@ uint32_t exhaustive_dense(cobsgpu_index* ix, const Slot& src, Slot& work, const 
         dp.slot_total = total1;
         dp.keys_out = work.d_cand.as<uint64_t>();
         ds_hist_kernel<<<grid, DS_THREADS, 0, st>>>(dp);
-        ds_scan_kernel<<<n, 256, 0, st>>>(dp);
+        ds_scan_kernel<<<n, 256 * DS_SCAN_GROUPS, 0, st>>>(dp);
         ds_scatter_kernel<<<grid, DS_THREADS, 0, st>>>(dp);
         CK(cudaGetLastError());
         ix->tm.kernel_launches += 3;
@@ -1480,6 +1484,85 @@ uint32_t exhaustive_dense(cobsgpu_index* ix, const Slot& src, Slot& work, const 
     }
     CK(cudaMemcpyAsync(work.o_flags(), src.d_flags(), 8, cudaMemcpyDeviceToDevice, st));
     return 0;
+}
+
+// Exhaustive lists whose lengths are known beforehand (threshold <= 0: every real document is a
+// result, cut at `limit`): the result volume -- 8 bytes per document per query over PCIe -- is
+// the bound, so the batch is cut into sub-batches of a few tens of megabytes and the copy of
+// one overlaps K2 + the counting sort of the next (two result areas, copies on s_fix).  The
+// doc[] | score[] arrays are assembled directly in the slot's pinned buffer and handed out.
+// Returns false when the batch is not worth splitting (the caller's one-pass path serves it).
+bool exhaustive_pipelined(cobsgpu_index* ix, const Slot& src, const std::vector<uint32_t>& ids,
+                          uint64_t limit, size_t sub_max, std::vector<HostList>* lists,
+                          std::vector<std::pair<uint32_t, uint32_t>>* where, bool ksplit,
+                          PinBuf* res_pin) {
+    static const bool off = std::getenv("COBSGPU_NO_PIPE") != nullptr;   // experiments only
+    const uint64_t real = ix->shard_real_docs;
+    const uint64_t per_q = limit ? std::min<uint64_t>(limit, real) : real;
+    const size_t nq = ids.size();
+    if (off || per_q == 0 || ix->pages.empty()) return false;
+    // Sub-batch size: every pass costs a few launches of fixed latency, and the first pass and the
+    // last copy overlap nothing -- so at least "pipe_kb" (32 MB) of results per copy, and at most
+    // about eight sub-batches.  A batch that fits one pass and is too short to split is left to
+    // the caller's one-pass path.
+    const size_t sub = std::min<size_t>(
+        sub_max, std::max<uint64_t>(div_ceil<uint64_t>(nq, 8),
+                                    std::max<uint64_t>(1, div_ceil<uint64_t>(ix->pipe_bytes, per_q * 8))));
+    if (nq < 2 * sub && nq <= sub_max) return false;
+    cudaStream_t st = ix->stream, sc = ix->s_fix;
+    Slot& work = ix->aux;
+    PassPlan pl;
+    pl.cap = static_cast<uint32_t>(std::max<uint64_t>(real, 1));
+    pl.limit = limit;
+    pl.mode = MODE_DENSE32;
+    const size_t ob = out_bytes(work, static_cast<uint32_t>(sub), pl);
+    work.d_out.ensure(ob);
+    work.d_out_alt.ensure(ob);
+    const size_t n_sub = div_ceil<size_t>(nq, sub);
+    const uint64_t total = static_cast<uint64_t>(nq) * per_q;
+    res_pin->ensure(total * 8);
+    work.h_out.ensure(std::max<size_t>(work.out_keys, n_sub * 8));
+    uint32_t* res_doc = res_pin->as<uint32_t>();
+    uint32_t* res_score = res_doc + total;
+    uint64_t* h_tot = work.h_out.as<uint64_t>();
+    for (size_t i = 0, b = 0; b < nq; ++i, b += sub) {
+        const uint32_t n = static_cast<uint32_t>(std::min(sub, nq - b));
+        const int buf = static_cast<int>(i & 1);
+        // work.d_out is result area `buf` from here on
+        std::swap(work.d_out.p, work.d_out_alt.p);
+        std::swap(work.d_out.cap, work.d_out_alt.cap);
+        if (i >= 2) CK(cudaStreamWaitEvent(st, work.ev_pipe[2 + buf], 0));   // its last copy has left
+        const uint32_t* d_ql = upload_qlist(work, ids, b, n, st);
+        uint32_t max_T = 1;
+        for (size_t j = 0; j < n; ++j) max_T = std::max(max_T, src.koff[ids[b + j] + 1] - src.koff[ids[b + j]]);
+        out_bytes(work, n, pl);   // (header layout for n queries)
+        if (exhaustive_dense(ix, src, work, d_ql, n, max_T, limit, ksplit, 0, st) != 0)
+            throw Err{ COBSGPU_ERR_CUDA, "exhaustive pass emitted candidates without a threshold" };
+        CK(cudaEventRecord(work.ev(work.ev_pipe[buf]), st));
+        CK(cudaStreamWaitEvent(sc, work.ev_pipe[buf], 0));
+        {
+            PhaseScope ps(ix, PH_D2H, sc);
+            const uint64_t m = static_cast<uint64_t>(n) * per_q;
+            const uint32_t* d_doc = reinterpret_cast<const uint32_t*>(work.o_keys());
+            CK(cudaMemcpyAsync(res_doc + b * per_q, d_doc, m * 4, cudaMemcpyDeviceToHost, sc));
+            CK(cudaMemcpyAsync(res_score + b * per_q, d_doc + m, m * 4, cudaMemcpyDeviceToHost, sc));
+            CK(cudaMemcpyAsync(h_tot + i, work.o_off() + n, 8, cudaMemcpyDeviceToHost, sc));
+        }
+        CK(cudaEventRecord(work.ev(work.ev_pipe[2 + buf]), sc));
+    }
+    CK(cudaStreamSynchronize(sc));
+    for (size_t i = 0, b = 0; b < nq; ++i, b += sub)
+        if (h_tot[i] != std::min(sub, nq - b) * per_q)
+            throw Err{ COBSGPU_ERR_CUDA, "exhaustive list length differs from the number of documents" };
+    lists->emplace_back();
+    HostList& L = lists->back();
+    L.off.resize(nq + 1);
+    for (size_t i = 0; i <= nq; ++i) L.off[i] = i * per_q;
+    L.doc.alias(res_doc, total);
+    L.score.alias(res_score, total);
+    for (size_t i = 0; i < nq; ++i)
+        (*where)[ids[i]] = { static_cast<uint32_t>(lists->size() - 1), static_cast<uint32_t>(i) };
+    return true;
 }
 
 // Synchronous exhaustive pass over the given queries of the batch in `src`, in workspace-bounded
@@ -1515,6 +1598,9 @@ void run_exhaustive(cobsgpu_index* ix, const Slot& src, const std::vector<uint32
         }
         const size_t sub = static_cast<size_t>(
             std::max<uint64_t>(1, std::min<uint64_t>(list.size(), ix->workspace_bytes / std::max<uint64_t>(per_q, 1))));
+        if (!huge && res_pin != nullptr && src.threshold <= 0.0 && list.size() == ids.size() &&
+            exhaustive_pipelined(ix, src, list, limit, sub, lists, where, ksplit, res_pin))
+            continue;
         for (size_t b = 0; b < list.size(); b += sub) {
             const uint32_t n = static_cast<uint32_t>(std::min(sub, list.size() - b));
             const uint32_t* d_ql = upload_qlist(work, list, b, n, st);
@@ -2524,6 +2610,7 @@ int cobsgpu_set_option(cobsgpu_index* ix, const char* name, int64_t value) {
         if (n == "max_candidates" && value >= 1) ix->max_candidates = static_cast<uint32_t>(std::min<int64_t>(value, 1 << 24));
         else if (n == "max_batch" && value >= 1) ix->max_batch = static_cast<uint32_t>(std::min<int64_t>(value, 1 << 22));
         else if (n == "workspace_mb" && value >= 1) ix->workspace_bytes = static_cast<uint64_t>(value) << 20;
+        else if (n == "pipe_kb" && value >= 1) ix->pipe_bytes = static_cast<uint64_t>(value) << 10;
         else if (n == "timing") ix->timing = value != 0;
         else if (n == "prefetch") ix->prefetch = value != 0;
         else if (n == "inputs_ready") ix->inputs_ready = value != 0;

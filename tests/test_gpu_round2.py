@@ -239,6 +239,40 @@ def test_exhaustive_lists_counting_sort(kind, n_docs, sig, h, ps):
 
 
 @pytest.mark.parametrize("kind,n_docs,sig,h,ps", [
+    (KIND_CLASSIC, 70000, [53], 3, 0), (KIND_CLASSIC, 5000, [301], 1, 0),
+    (KIND_COMPACT, 40000, [61, 97, 31, 43, 59], 3, 1024),
+])
+def test_exhaustive_lists_in_pipelined_sub_batches(kind, n_docs, sig, h, ps):
+    """lists of every document (threshold 0): the batch is cut into sub-batches whose result
+    copies overlap the next sub-batch's kernels; "pipe_kb" makes the sub-batches small enough
+    for a test index.  Ragged last sub-batch, mixed one- and two-byte counts, limits, a following
+    call that reuses the pinned result buffer, and the submit/collect form."""
+    g, o = pair(kind, n_docs, sig, h, page_size=ps, seed=n_docs + 33)
+    lens = [100, 45, 285, 286, 1030, 31 if h > 1 else 40, 77, 300, 64, 2000, 100]
+    qs = [rq(n_docs + 50 + i, L) for i, L in enumerate(lens)]
+    want = {k: [oracle.search(o, q, 0.0, k) for q in qs] for k in (0, 3000)}
+    for pipe_kb in (1, 3 * n_docs * 8 // 1024 + 1, 4 * n_docs * 8 // 1024 + 1):   # 1, 3-4, 4-5 queries per copy
+        g.set_option("pipe_kb", pipe_kb)
+        for k in (0, 3000):
+            for q, r, w in zip(qs, g.search_batch(qs, 0.0, k), want[k]):
+                assert as_list(r) == w, (pipe_kb, k, len(q))
+        # a shorter batch next: the buffers of the previous call are reused
+        for q, r, w in zip(qs[:5], g.search_batch(qs[:5], -1.0, 0), want[0]):
+            assert as_list(r) == w, (pipe_kb, len(q))
+    g.set_option("pipe_kb", 1)
+    tickets = []
+    for a, b in ((0, 4), (4, 11)):
+        blob = np.frombuffer(b"".join(qs[a:b]), dtype=np.uint8).copy()
+        off = np.zeros(b - a + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(q) for q in qs[a:b]])
+        tickets.append(g.submit(blob, off, 0.0, 0))
+    got = [g.collect(t) for t in tickets]
+    for r, w in zip(got[0] + got[1], want[0]):
+        assert as_list(r) == w
+    g.close()
+
+
+@pytest.mark.parametrize("kind,n_docs,sig,h,ps", [
     (KIND_CLASSIC, 70000, [53], 3, 0), (KIND_COMPACT, 40000, [61, 97, 31, 43, 59], 3, 1024),
     (KIND_CLASSIC, 129, [333], 4, 0),
 ])
