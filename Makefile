@@ -46,7 +46,7 @@ build/host_unit_tests: cobs_b200/host/tests/host_unit_tests.cpp build/libcobs_b2
 
 # host-side unit tests of the __host__ __device__ kernel arithmetic (test infrastructure: links
 # the oracle)
-build/kernel_unit_tests: tests/csrc/kernel_unit_tests.cu $(wildcard $(CSRC)/*.cuh) oracle
+build/kernel_unit_tests: tests/csrc/kernel_unit_tests.cu $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.hpp) oracle
 	@mkdir -p build
 	$(NVCC) $(ARCH) -O2 -std=c++17 --expt-relaxed-constexpr --extended-lambda -Xcompiler -Wno-unknown-pragmas \
 	    -o $@ $< -Loracle -loracle -Xlinker -rpath -Xlinker '$$ORIGIN/../oracle' 2> build/kut.log || (cat build/kut.log; false)

@@ -34,6 +34,7 @@
 #include "fill.cuh"
 #include "hash.cuh"
 #include "index_file.hpp"
+#include "merge_runs.hpp"
 #include "score.cuh"
 #include "select.cuh"
 
@@ -208,7 +209,6 @@ struct U32Buf {
     uint32_t* begin() { return p; }
     uint32_t* end() { return p + n; }
     const uint32_t* begin() const { return p; }
-    uint32_t& operator[](size_t i) { return p[i]; }
     const uint32_t& operator[](size_t i) const { return p[i]; }
     void push_back(uint32_t v) {
         reserve(n + 1);
@@ -1227,11 +1227,11 @@ void launch_select(cobsgpu_index* ix, const Slot& src, Slot& work, const uint32_
         }
     }
     const size_t smem = static_cast<size_t>(fp.fin_sort_max) * 8;
-    static bool attr_set[64] = {};
-    if (!attr_set[ix->device & 63]) {
+    static std::atomic<bool> attr_set[64];   // (shards of a group collect on threads of their own)
+    if (!attr_set[ix->device & 63].load()) {
         CK(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(FIN_SORT_MAX * 8)));
-        attr_set[ix->device & 63] = true;
+        attr_set[ix->device & 63].store(true);
     }
     finalize_kernel<<<div_ceil<uint32_t>(n_slots, FIN_WARPS), FIN_WARPS * 32, smem, st>>>(fp);
     CK(cudaGetLastError());
@@ -2033,6 +2033,7 @@ struct cobsgpu_group {
 namespace {
 
 using GSlot = cobsgpu_group::GSlot;
+static_assert(MERGE_RUNS_MAX_LISTS >= MERGE_MAX_LISTS, "merge_runs holds one cursor per shard");
 
 void group_finish_open(cobsgpu_group* grp) {
     const size_t n = grp->shards.size();
@@ -2210,6 +2211,78 @@ void host_merge(std::vector<uint64_t>& keys, uint64_t limit) {
     if (limit && keys.size() > limit) keys.resize(limit);
 }
 
+// A group batch whose lists hold every document (threshold <= 0 without a small limit): every
+// shard collects on a host thread of its own -- the exhaustive passes run inside collect, so the
+// GPUs work side by side instead of one after the other -- and the shards' lists are merged run
+// by run, queries spread over host threads.
+void group_collect_exhaustive(cobsgpu_group* grp, GSlot& gsl) {
+    const uint32_t n = static_cast<uint32_t>(grp->shards.size());
+    const uint32_t nq = gsl.nq;
+    std::vector<Err> errs(n, Err{ COBSGPU_OK, "" });
+    auto collect_one = [&](uint32_t g) {
+        try {
+            cobsgpu_index* ix = grp->shards[g];
+            CK(cudaSetDevice(ix->device));
+            collect_batch(ix, *gsl.sl[g]);
+        } catch (const Err& e) {
+            errs[g] = e;
+        } catch (const std::bad_alloc&) {
+            errs[g] = Err{ COBSGPU_ERR_OOM, "host out of memory" };
+        } catch (const std::exception& e) {
+            errs[g] = Err{ COBSGPU_ERR_INVALID_ARG, e.what() };
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        for (uint32_t g = 1; g < n; ++g) th.emplace_back(collect_one, g);
+        collect_one(0);
+        for (auto& t : th) t.join();
+    }
+    for (uint32_t g = 0; g < n; ++g)
+        if (errs[g].code != COBSGPU_OK) {
+            // an invalid base is reported by every shard: keep the message of the first
+            throw errs[g];
+        }
+    gsl.r_off.resize(static_cast<size_t>(nq) + 1);
+    gsl.r_off[0] = 0;
+    for (uint32_t i = 0; i < nq; ++i) {
+        uint64_t len = 0;
+        for (uint32_t g = 0; g < n; ++g) len += gsl.sl[g]->r_off[i + 1] - gsl.sl[g]->r_off[i];
+        if (gsl.limit && len > gsl.limit) len = gsl.limit;
+        gsl.r_off[i + 1] = gsl.r_off[i] + len;
+    }
+    const uint64_t total = gsl.r_off[nq];
+    gsl.r_doc.resize(total);
+    gsl.r_score.resize(total);
+    auto merge_range = [&](uint32_t q0, uint32_t q1) {
+        const uint32_t* doc[MERGE_MAX_LISTS];
+        const uint32_t* score[MERGE_MAX_LISTS];
+        uint64_t len[MERGE_MAX_LISTS];
+        for (uint32_t i = q0; i < q1; ++i) {
+            for (uint32_t g = 0; g < n; ++g) {
+                const Slot& sl = *gsl.sl[g];
+                doc[g] = sl.r_doc.begin() + sl.r_off[i];
+                score[g] = sl.r_score.begin() + sl.r_off[i];
+                len[g] = sl.r_off[i + 1] - sl.r_off[i];
+            }
+            merge_runs(n, doc, score, len, gsl.r_off[i + 1] - gsl.r_off[i], gsl.r_doc.data() + gsl.r_off[i],
+                       gsl.r_score.data() + gsl.r_off[i]);
+        }
+    };
+    unsigned hw = std::thread::hardware_concurrency();
+    const uint32_t nt = static_cast<uint32_t>(std::min<uint64_t>(
+        std::min<uint32_t>(nq, std::max(1u, std::min(hw, 8u))), std::max<uint64_t>(1, total >> 18)));
+    if (nt <= 1) {
+        merge_range(0, nq);
+    } else {
+        std::vector<std::thread> th;
+        for (uint32_t t = 0; t < nt; ++t)
+            th.emplace_back(merge_range, static_cast<uint32_t>(static_cast<uint64_t>(nq) * t / nt),
+                            static_cast<uint32_t>(static_cast<uint64_t>(nq) * (t + 1) / nt));
+        for (auto& t : th) t.join();
+    }
+}
+
 void group_collect(cobsgpu_group* grp, GSlot& gsl) {
     if (!gsl.busy) throw Err{ COBSGPU_ERR_INVALID_ARG, "group batch is not in flight" };
     const uint32_t n = static_cast<uint32_t>(grp->shards.size());
@@ -2226,14 +2299,15 @@ void group_collect(cobsgpu_group* grp, GSlot& gsl) {
     gsl.r_off.assign(1, 0);
     gsl.r_doc.clear();
     gsl.r_score.clear();
-    // queries that need the per-shard host path: all of them (mode -1) or the flagged ones
+    if (gsl.mode < 0) {   // every list holds every document: per-shard collects + host merge
+        group_collect_exhaustive(grp, gsl);
+        return;
+    }
+    // queries that need the per-shard host path: the flagged ones
     std::vector<uint32_t> redo;
     std::vector<uint64_t> off_main;
     const uint64_t* keys_main = nullptr;
-    if (gsl.mode < 0) {
-        redo.resize(nq);
-        for (uint32_t i = 0; i < nq; ++i) redo[i] = i;
-    } else {
+    {
         cobsgpu_index* lead = grp->shards[0];
         Slot& ls = *gsl.sl[0];
         CK(cudaSetDevice(lead->device));
@@ -2269,17 +2343,7 @@ void group_collect(cobsgpu_group* grp, GSlot& gsl) {
     }
     // per-shard host path for the remaining queries + merge on the host
     std::vector<std::vector<uint64_t>> merged(redo.size());
-    if (gsl.mode < 0) {
-        for (uint32_t g = 0; g < n; ++g) {
-            cobsgpu_index* ix = grp->shards[g];
-            CK(cudaSetDevice(ix->device));
-            Slot& sl = *gsl.sl[g];
-            collect_batch(ix, sl);
-            for (uint32_t i = 0; i < nq; ++i)
-                for (uint64_t e = sl.r_off[i]; e < sl.r_off[i + 1]; ++e)
-                    merged[i].push_back(make_key(sl.r_score[e], sl.r_doc[e]));
-        }
-    } else {
+    {
         // flagged queries: re-run them through every shard's own host path (which falls back
         // to its exhaustive pass), straight from the hashes still resident in the shard's slot
         for (uint32_t g = 0; g < n; ++g) {

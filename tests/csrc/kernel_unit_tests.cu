@@ -12,6 +12,7 @@
 
 #include "../../cobs_b200/csrc/common.cuh"
 #include "../../cobs_b200/csrc/hash.cuh"
+#include "../../cobs_b200/csrc/merge_runs.hpp"
 #include "../../cobs_b200/csrc/score.cuh"
 #include "../../oracle/cobs_oracle.h"
 
@@ -55,8 +56,54 @@ static void check_fixed(std::mt19937_64& rng, int canon) {
     }
 }
 
+
+// merge_runs (group path, lists of every document): random partitions of a scored document set
+// into shards -- contiguous blocks, interleaved blocks, single documents -- merged back and
+// compared with a plain sort under the reference order (score desc, document asc)
+static void check_merge_runs(std::mt19937_64& rng) {
+    for (int it = 0; it < 300; ++it) {
+        const uint32_t n_docs = it < 10 ? it : 1 + rng() % 5000;
+        const uint32_t n_lists = 1 + rng() % 16;
+        const uint32_t max_score = it % 3 == 0 ? 1 : (it % 3 == 1 ? 7 : 70000);
+        const uint32_t block = it % 4 == 0 ? 1 : 1 + rng() % 700;   // documents per column block
+        std::vector<uint64_t> all;
+        std::vector<std::vector<uint64_t>> part(n_lists);
+        for (uint32_t d = 0; d < n_docs; ++d) {
+            const uint64_t k = make_key(static_cast<uint32_t>(rng() % (max_score + 1)), d * 3 + 1);
+            all.push_back(k);
+            const uint32_t owner = it % 2 ? (d / block) % n_lists : static_cast<uint32_t>(static_cast<uint64_t>(d) * n_lists / n_docs);
+            part[owner].push_back(k);
+        }
+        std::sort(all.begin(), all.end());
+        std::vector<std::vector<uint32_t>> docs(n_lists), scores(n_lists);
+        const uint32_t* dp[16];
+        const uint32_t* sp[16];
+        uint64_t len[16];
+        for (uint32_t g = 0; g < n_lists; ++g) {
+            std::sort(part[g].begin(), part[g].end());
+            for (uint64_t k : part[g]) {
+                docs[g].push_back(key_doc(k));
+                scores[g].push_back(key_score(k));
+            }
+            dp[g] = docs[g].data();
+            sp[g] = scores[g].data();
+            len[g] = part[g].size();
+        }
+        for (uint64_t want : { static_cast<uint64_t>(n_docs), static_cast<uint64_t>(n_docs / 3), static_cast<uint64_t>(1), static_cast<uint64_t>(0) }) {
+            want = std::min<uint64_t>(want, n_docs);
+            std::vector<uint32_t> od(want + 1, 0xABABABABu), os(want + 1, 0xABABABABu);
+            merge_runs(n_lists, dp, sp, len, want, od.data(), os.data());
+            bool same = od[want] == 0xABABABABu && os[want] == 0xABABABABu;   // nothing written beyond
+            for (uint64_t i = 0; i < want && same; ++i)
+                same = od[i] == key_doc(all[i]) && os[i] == key_score(all[i]);
+            CHECK(same);
+        }
+    }
+}
+
 int main() {
     std::mt19937_64 rng(12345);
+    check_merge_runs(rng);
 
     // XXH64 through the byte getter: all lengths 0..200, random seeds
     for (uint32_t len = 0; len <= 200; ++len) {
