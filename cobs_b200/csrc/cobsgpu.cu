@@ -209,11 +209,6 @@ struct U32Buf {
     uint32_t* begin() { return p; }
     uint32_t* end() { return p + n; }
     const uint32_t* begin() const { return p; }
-    const uint32_t& operator[](size_t i) const { return p[i]; }
-    void push_back(uint32_t v) {
-        reserve(n + 1);
-        p[n++] = v;
-    }
     // append [first, last); `where` must be end()
     void insert(const uint32_t*, const uint32_t* first, const uint32_t* last) {
         const size_t m = static_cast<size_t>(last - first);
@@ -2205,12 +2200,6 @@ GSlot& group_submit(cobsgpu_group* grp, const char* queries, const uint64_t* off
     return gsl;
 }
 
-// merges per-shard host lists of one query (each ordered) into `out` under the global order
-void host_merge(std::vector<uint64_t>& keys, uint64_t limit) {
-    std::sort(keys.begin(), keys.end());
-    if (limit && keys.size() > limit) keys.resize(limit);
-}
-
 // A group batch whose lists hold every document (threshold <= 0 without a small limit): every
 // shard collects on a host thread of its own -- the exhaustive passes run inside collect, so the
 // GPUs work side by side instead of one after the other -- and the shards' lists are merged run
@@ -2341,42 +2330,45 @@ void group_collect(cobsgpu_group* grp, GSlot& gsl) {
             return;
         }
     }
-    // per-shard host path for the remaining queries + merge on the host
-    std::vector<std::vector<uint64_t>> merged(redo.size());
-    {
-        // flagged queries: re-run them through every shard's own host path (which falls back
-        // to its exhaustive pass), straight from the hashes still resident in the shard's slot
-        for (uint32_t g = 0; g < n; ++g) {
-            cobsgpu_index* ix = grp->shards[g];
-            CK(cudaSetDevice(ix->device));
-            std::vector<HostList> lists;
-            std::vector<std::pair<uint32_t, uint32_t>> where(nq, { 0u, 0u });
-            run_exhaustive(ix, *gsl.sl[g], redo, gsl.limit, &lists, &where);
-            for (size_t j = 0; j < redo.size(); ++j) {
-                const HostList& L = lists[where[redo[j]].first];
-                const uint32_t s = where[redo[j]].second;
-                for (uint64_t e = L.off[s]; e < L.off[s + 1]; ++e)
-                    merged[j].push_back(make_key(L.score[e], L.doc[e]));
-            }
-        }
+    // flagged queries: re-run them through every shard's own host path (which falls back to its
+    // exhaustive pass), straight from the hashes still resident in the shard's slot, and merge
+    // the shards' lists on the host
+    std::vector<std::vector<HostList>> lists(n);
+    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> where(
+        n, std::vector<std::pair<uint32_t, uint32_t>>(nq, { 0u, 0u }));
+    for (uint32_t g = 0; g < n; ++g) {
+        cobsgpu_index* ix = grp->shards[g];
+        CK(cudaSetDevice(ix->device));
+        run_exhaustive(ix, *gsl.sl[g], redo, gsl.limit, &lists[g], &where[g]);
     }
-    for (auto& m : merged) host_merge(m, gsl.limit);
     size_t rj = 0;
     uint64_t run = 0;
     for (uint32_t i = 0; i < nq; ++i) {
         if (rj < redo.size() && redo[rj] == i) {
-            for (uint64_t key : merged[rj]) {
-                gsl.r_doc.push_back(key_doc(key));
-                gsl.r_score.push_back(key_score(key));
+            const uint32_t* doc[MERGE_MAX_LISTS];
+            const uint32_t* score[MERGE_MAX_LISTS];
+            uint64_t len[MERGE_MAX_LISTS];
+            uint64_t sum = 0;
+            for (uint32_t g = 0; g < n; ++g) {
+                const HostList& L = lists[g][where[g][i].first];
+                const uint32_t s = where[g][i].second;
+                doc[g] = L.doc.begin() + L.off[s];
+                score[g] = L.score.begin() + L.off[s];
+                len[g] = L.off[s + 1] - L.off[s];
+                sum += len[g];
             }
-            run += merged[rj].size();
+            if (gsl.limit && sum > gsl.limit) sum = gsl.limit;
+            gsl.r_doc.resize(run + sum);
+            gsl.r_score.resize(run + sum);
+            merge_runs(n, doc, score, len, sum, gsl.r_doc.data() + run, gsl.r_score.data() + run);
+            run += sum;
             ++rj;
         } else {
-            for (uint64_t e = off_main[i]; e < off_main[i + 1]; ++e) {
-                gsl.r_doc.push_back(key_doc(keys_main[e]));
-                gsl.r_score.push_back(key_score(keys_main[e]));
-            }
-            run += off_main[i + 1] - off_main[i];
+            const uint64_t a = off_main[i], m = off_main[i + 1] - off_main[i];
+            gsl.r_doc.resize(run + m);
+            gsl.r_score.resize(run + m);
+            decode_keys(keys_main + a, m, gsl.r_doc.data() + run, gsl.r_score.data() + run);
+            run += m;
         }
         gsl.r_off.push_back(run);
     }

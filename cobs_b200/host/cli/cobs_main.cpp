@@ -48,6 +48,21 @@ struct Batch {
     std::vector<std::string> comments, queries;
 };
 
+// COBS_CLI_TRACE=1: wall seconds per stage of `cobs query -f`, one extra line on stderr
+struct CliTrace {
+    bool on = std::getenv("COBS_CLI_TRACE") != nullptr;
+    double open = 0, parse = 0, wait = 0, search = 0, format = 0, write = 0;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    static double since(std::chrono::steady_clock::time_point t) {
+        return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count();
+    }
+    void print() const {
+        if (!on) return;
+        std::fprintf(stderr, "CLI open=%.3f parse=%.3f wait_for_worker=%.3f | worker: search=%.3f "
+                     "format=%.3f write=%.3f | wall=%.3f\n", open, parse, wait, search, format, write, since(t0));
+    }
+} g_trace;
+
 // "<comment>\t<count>\n" + "<doc>\t<score>\n" per result, formatted into one buffer per batch
 // and written with a single fwrite (operator<< per field costs more than the GPU search)
 void format_batch(const Batch& b, const std::vector<std::vector<cobs::SearchResult> >& results,
@@ -75,10 +90,16 @@ void format_batch(const Batch& b, const std::vector<std::vector<cobs::SearchResu
 void flush(cobs::Search& s, Batch& b, double threshold, unsigned num_results) {
     if (b.queries.empty()) return;
     std::vector<std::vector<cobs::SearchResult> > results;
+    auto t = std::chrono::steady_clock::now();
     s.search_batch(b.queries, results, threshold, num_results);
+    g_trace.search += CliTrace::since(t);
+    t = std::chrono::steady_clock::now();
     std::string out;
     format_batch(b, results, out);
+    g_trace.format += CliTrace::since(t);
+    t = std::chrono::steady_clock::now();
     std::cout.write(out.data(), std::streamsize(out.size()));
+    g_trace.write += CliTrace::since(t);
     b.comments.clear();
     b.queries.clear();
 }
@@ -98,8 +119,13 @@ void process_query(cobs::Search& s, double threshold, unsigned num_results,
         std::string line, query, comment;
         Batch parsing, searching;
         std::future<void> worker;
+        auto t_parse = std::chrono::steady_clock::now();
         auto dispatch = [&] {
+            g_trace.parse += CliTrace::since(t_parse);
+            auto t_wait = std::chrono::steady_clock::now();
             if (worker.valid()) worker.get();      // batch i-1 is written before batch i starts
+            g_trace.wait += CliTrace::since(t_wait);
+            t_parse = std::chrono::steady_clock::now();
             std::swap(parsing, searching);
             worker = std::async(std::launch::async,
                                 [&] { flush(s, searching, threshold, num_results); });
@@ -123,13 +149,16 @@ void process_query(cobs::Search& s, double threshold, unsigned num_results,
         }
         if (!query.empty()) push();
         dispatch();
+        auto t_wait = std::chrono::steady_clock::now();
         if (worker.valid()) worker.get();
+        g_trace.wait += CliTrace::since(t_wait);
     }
     else {
         cobs::die_with_message("Pass a verbatim query or a query file.");
     }
     std::cout.flush();
     s.timer().print("search");
+    g_trace.print();
 }
 
 int query(int argc, char** argv) {
@@ -185,6 +214,7 @@ int query(int argc, char** argv) {
             cobs::die_with_message("Could not open index path \"" + path + "\"");
     }
     cobs::ClassicSearch s(indices);
+    g_trace.open = CliTrace::since(g_trace.t0);
     process_query(s, threshold, num_results, query, query_file, batch);
     return 0;
 }

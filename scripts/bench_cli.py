@@ -26,13 +26,16 @@ raw = blob.tobytes()
 with open(fa, "w") as f:
     for i in range(nq):
         f.write(">q%d\n%s\n" % (i, raw[i * 100:(i + 1) * 100].decode()))
-for batch in ("4096", "16384", "65536"):
+env = dict(os.environ, COBS_CLI_TRACE="1")
+for batch in os.environ.get("BATCHES", "16384,4096,65536,16384").split(","):
     t0 = time.perf_counter()
     r = subprocess.run([os.path.join(ROOT, "build", "cobs"), "query", "-i", idx, "-f", fa, "-t", thr,
-                        "--batch", batch], stdout=open("/dev/shm/cli_bench.out", "w"), stderr=subprocess.PIPE, text=True)
+                        "--batch", batch], stdout=open("/dev/shm/cli_bench.out", "w"), stderr=subprocess.PIPE,
+                       text=True, env=env)
     dt = time.perf_counter() - t0
     out_bytes = os.path.getsize("/dev/shm/cli_bench.out")
-    print("batch %s: wall %.2f s (%.0f queries/s incl. load), stdout %.1f MB, rc %d | %s" % (
-        batch, dt, nq / dt, out_bytes / 1e6, r.returncode, r.stderr.strip().splitlines()[-1][:300]), flush=True)
+    lines = [l for l in r.stderr.strip().splitlines() if l.startswith(("TIMER", "CLI "))]
+    print("batch %s: wall %.2f s (%.0f queries/s incl. load), stdout %.1f MB, rc %d\n    %s" % (
+        batch, dt, nq / dt, out_bytes / 1e6, r.returncode, "\n    ".join(l[:300] for l in lines)), flush=True)
 for p in (idx, fa, "/dev/shm/cli_bench.out"):
     os.unlink(p)
