@@ -41,7 +41,7 @@ void usage_query(std::ostream& os) {
           "  -T, --threads <n>    accepted for compatibility (the search runs on the GPU)\n"
           "      --gpus <n>       shard every index over n GPUs along the document axis\n"
           "      --device <d>     first CUDA device to use, default: 0\n"
-          "      --batch <n>      FASTA records per GPU batch, default: 4096\n";
+          "      --batch <n>      FASTA records per GPU batch, default: 16384\n";
 }
 
 struct Batch {
@@ -64,14 +64,20 @@ struct CliTrace {
 } g_trace;
 
 // "<comment>\t<count>\n" + "<doc>\t<score>\n" per result, formatted into one buffer per batch
-// and written with a single fwrite (operator<< per field costs more than the GPU search)
+// and written with a single write (operator<< per field costs more than the GPU search, and so
+// does snprintf: the digits are produced by hand)
 void format_batch(const Batch& b, const std::vector<std::vector<cobs::SearchResult> >& results,
                   std::string& out) {
     out.clear();
     char num[24];
     auto put_num = [&](unsigned long v) {
-        int n = std::snprintf(num, sizeof(num), "%lu", v);
-        out.append(num, size_t(n));
+        char* end = num + sizeof(num);
+        char* p = end;
+        do {
+            *--p = char('0' + v % 10);
+            v /= 10;
+        } while (v != 0);
+        out.append(p, size_t(end - p));
     };
     for (size_t i = 0; i < results.size(); ++i) {
         out += b.comments[i];
@@ -87,26 +93,26 @@ void format_batch(const Batch& b, const std::vector<std::vector<cobs::SearchResu
     }
 }
 
-void flush(cobs::Search& s, Batch& b, double threshold, unsigned num_results) {
-    if (b.queries.empty()) return;
+// one batch on its way through the stages: parsed records, then their results
+struct Stage {
+    Batch b;
     std::vector<std::vector<cobs::SearchResult> > results;
+};
+
+void write_stage(const Stage& st) {
     auto t = std::chrono::steady_clock::now();
-    s.search_batch(b.queries, results, threshold, num_results);
-    g_trace.search += CliTrace::since(t);
-    t = std::chrono::steady_clock::now();
     std::string out;
-    format_batch(b, results, out);
+    format_batch(st.b, st.results, out);
     g_trace.format += CliTrace::since(t);
     t = std::chrono::steady_clock::now();
     std::cout.write(out.data(), std::streamsize(out.size()));
     g_trace.write += CliTrace::since(t);
-    b.comments.clear();
-    b.queries.clear();
 }
 
 // same record splitting as process_query (src/cobs.cpp:425-462).  The FASTA file is processed as
-// a two-stage pipeline: this thread parses batch i+1 while a worker searches batch i on the GPU,
-// formats its lines and writes them -- in order, so stdout is what the reference prints.
+// a three-stage pipeline: this thread parses batch i+2 while one worker searches batch i+1 on the
+// GPU and another formats and writes the lines of batch i -- in order, so stdout is what the
+// reference prints.
 void process_query(cobs::Search& s, double threshold, unsigned num_results,
                    const std::string& query_line, const std::string& query_file, size_t batch) {
     if (!query_line.empty()) {
@@ -117,18 +123,27 @@ void process_query(cobs::Search& s, double threshold, unsigned num_results,
     else if (!query_file.empty()) {
         std::ifstream qf(query_file);
         std::string line, query, comment;
-        Batch parsing, searching;
-        std::future<void> worker;
+        Batch parsing;
+        std::future<void> searcher, writer;   // `writer` is only touched by the searcher tasks
         auto t_parse = std::chrono::steady_clock::now();
         auto dispatch = [&] {
             g_trace.parse += CliTrace::since(t_parse);
             auto t_wait = std::chrono::steady_clock::now();
-            if (worker.valid()) worker.get();      // batch i-1 is written before batch i starts
+            if (searcher.valid()) searcher.get();   // one search at a time, in order
             g_trace.wait += CliTrace::since(t_wait);
+            if (!parsing.queries.empty()) {
+                auto st = std::make_shared<Stage>();
+                st->b.comments.swap(parsing.comments);
+                st->b.queries.swap(parsing.queries);
+                searcher = std::async(std::launch::async, [&s, &writer, st, threshold, num_results] {
+                    auto t = std::chrono::steady_clock::now();
+                    s.search_batch(st->b.queries, st->results, threshold, num_results);
+                    g_trace.search += CliTrace::since(t);
+                    if (writer.valid()) writer.get();   // batch i-1 is written before batch i
+                    writer = std::async(std::launch::async, [st] { write_stage(*st); });
+                });
+            }
             t_parse = std::chrono::steady_clock::now();
-            std::swap(parsing, searching);
-            worker = std::async(std::launch::async,
-                                [&] { flush(s, searching, threshold, num_results); });
         };
         auto push = [&] {
             parsing.comments.push_back(comment);
@@ -150,7 +165,8 @@ void process_query(cobs::Search& s, double threshold, unsigned num_results,
         if (!query.empty()) push();
         dispatch();
         auto t_wait = std::chrono::steady_clock::now();
-        if (worker.valid()) worker.get();
+        if (searcher.valid()) searcher.get();
+        if (writer.valid()) writer.get();
         g_trace.wait += CliTrace::since(t_wait);
     }
     else {
@@ -166,7 +182,7 @@ int query(int argc, char** argv) {
     std::string query, query_file;
     double threshold = 0.8;
     unsigned num_results = 0;
-    size_t batch = 4096;
+    size_t batch = 16384;
 
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];

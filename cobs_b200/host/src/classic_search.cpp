@@ -140,6 +140,11 @@ void ClassicSearch::search_batch(
     }
     std::string blob;
     std::vector<uint64_t> offsets(nq + 1, 0);
+    {
+        size_t bytes = 0;
+        for (const std::string& q : queries) bytes += q.size();
+        blob.reserve(bytes);
+    }
     for (size_t i = 0; i < nq; ++i) {
         assert_exit(queries[i].size() >= max_term_size,
                     "query too short, needs to be at least "
