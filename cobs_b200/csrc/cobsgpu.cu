@@ -965,6 +965,7 @@ static constexpr int FLAG_CLEAR = 0x7F7F7F7F;
 static constexpr uint32_t MAX_T_SHORT = 255;      // 8 bit-planes
 static constexpr uint32_t MAX_T_LONG = 65535;     // 16 bit-planes
 static constexpr uint32_t TOPK_MAX_K = 1024;      // largest -l served by the per-warp top-k epilogue
+static constexpr uint64_t PINNED_RESULT_MAX = 4ull << 30;   // result bytes handed out from pinned memory
 
 // Fills slot `sl` with queries [q0, q1) of the caller's batch: host geometry, upload of the
 // queries (unless they already live on the device) and of the metadata block, K1 -- all on `st`.
@@ -1496,6 +1497,9 @@ bool exhaustive_pipelined(cobsgpu_index* ix, const Slot& src, const std::vector<
     const uint64_t per_q = limit ? std::min<uint64_t>(limit, real) : real;
     const size_t nq = ids.size();
     if (off || per_q == 0 || ix->pages.empty()) return false;
+    // the arrays handed out are page-locked (~0.7 s per GB the first time a slot grows to a
+    // size): beyond a few GB per call the general path's pageable arrays are the better deal
+    if (static_cast<uint64_t>(ids.size()) * per_q * 8 > PINNED_RESULT_MAX) return false;
     // Sub-batch size: every pass costs a few launches of fixed latency, and the first pass and the
     // last copy overlap nothing -- so at least "pipe_kb" (32 MB) of results per copy, and at most
     // about eight sub-batches.  A batch that fits one pass and is too short to split is left to
@@ -1645,7 +1649,8 @@ void run_exhaustive(cobsgpu_index* ix, const Slot& src, const std::vector<uint32
             // One pass that covers the whole batch and came out as doc[] | score[]: the arrays land
             // in the batch slot's own pinned buffer and are handed out as they are -- for lists of
             // every document of a large index, unpacking and copying cost more than the search.
-            const bool hand_out = soa && res_pin != nullptr && sub >= list.size() && list.size() == ids.size();
+            const bool hand_out = soa && res_pin != nullptr && sub >= list.size() && list.size() == ids.size() &&
+                                  total * 8 <= PINNED_RESULT_MAX;
             if (hand_out && total) {
                 res_pin->ensure(total * 8);
                 {
@@ -1925,6 +1930,13 @@ void collect_batch(cobsgpu_index* ix, Slot& sl) {
         return;
     }
     uint64_t run = 0;
+    for (uint32_t i = 0; i < nq; ++i) {
+        const HostList& L = lists[where[i].first];
+        run += L.off[where[i].second + 1] - L.off[where[i].second];
+    }
+    sl.r_doc.reserve(run);     // one allocation, not a chain of growing copies
+    sl.r_score.reserve(run);
+    run = 0;
     for (uint32_t i = 0; i < nq; ++i) {
         const HostList& L = lists[where[i].first];
         const uint32_t s = where[i].second;
