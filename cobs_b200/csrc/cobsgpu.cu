@@ -965,7 +965,7 @@ static constexpr int FLAG_CLEAR = 0x7F7F7F7F;
 static constexpr uint32_t MAX_T_SHORT = 255;      // 8 bit-planes
 static constexpr uint32_t MAX_T_LONG = 65535;     // 16 bit-planes
 static constexpr uint32_t TOPK_MAX_K = 1024;      // largest -l served by the per-warp top-k epilogue
-static constexpr uint64_t PINNED_RESULT_MAX = 4ull << 30;   // result bytes handed out from pinned memory
+static constexpr uint64_t PINNED_RESULT_MAX = 2ull << 30;   // result bytes handed out from pinned memory
 
 // Fills slot `sl` with queries [q0, q1) of the caller's batch: host geometry, upload of the
 // queries (unless they already live on the device) and of the metadata block, K1 -- all on `st`.
@@ -2630,6 +2630,7 @@ int cobsgpu_index_save(const cobsgpu_index* ix, const char* path) {
                 put(buf.data(), buf.size());
             }
         }
+        if (std::fflush(f) != 0) throw Err{ COBSGPU_ERR_IO, "write failed" };
     });
 }
 
