@@ -205,6 +205,7 @@ struct U32Buf {
         }
         n = 0;
     }
+    size_t size() const { return n; }
     uint32_t* data() { return p; }
     uint32_t* begin() { return p; }
     uint32_t* end() { return p + n; }
@@ -378,6 +379,7 @@ struct cobsgpu_index {
     uint32_t max_batch = 16384;
     uint64_t workspace_bytes = 1024ull << 20;
     uint64_t pipe_bytes = 32ull << 20;    // result bytes per copy of the pipelined exhaustive passes
+    uint64_t pinned_result_max = 2ull << 30;   // result bytes per call handed out from pinned memory
     bool timing = false;
 
     // execution state: three streams so that consecutive batches overlap -- s_in uploads the
@@ -965,7 +967,6 @@ static constexpr int FLAG_CLEAR = 0x7F7F7F7F;
 static constexpr uint32_t MAX_T_SHORT = 255;      // 8 bit-planes
 static constexpr uint32_t MAX_T_LONG = 65535;     // 16 bit-planes
 static constexpr uint32_t TOPK_MAX_K = 1024;      // largest -l served by the per-warp top-k epilogue
-static constexpr uint64_t PINNED_RESULT_MAX = 2ull << 30;   // result bytes handed out from pinned memory
 
 // Fills slot `sl` with queries [q0, q1) of the caller's batch: host geometry, upload of the
 // queries (unless they already live on the device) and of the metadata block, K1 -- all on `st`.
@@ -1304,24 +1305,33 @@ struct HostList {
     U32Buf doc, score;
 };
 
-void decode_keys(const uint64_t* keys, uint64_t n, uint32_t* doc, uint32_t* score) {
-    auto part = [=](uint64_t a, uint64_t b) {
-        for (uint64_t i = a; i < b; ++i) {
-            doc[i] = key_doc(keys[i]);
-            score[i] = key_score(keys[i]);
-        }
-    };
-    // exhaustive lists of large indices are memory-bound on the host: split them over threads
+// fn(a, b) over [0, n) in a few host threads: result lists of large indices are memory-bound on
+// the host, one thread does not saturate it
+template <typename F>
+void split_over_threads(uint64_t n, F&& fn) {
     const uint64_t per_thread = 1ull << 20;
     unsigned hw = std::thread::hardware_concurrency();
     const uint64_t nt = std::min<uint64_t>(std::max(1u, std::min(hw, 8u)), n / per_thread);
     if (nt <= 1) {
-        part(0, n);
+        fn(static_cast<uint64_t>(0), n);
         return;
     }
     std::vector<std::thread> th;
-    for (uint64_t t = 0; t < nt; ++t) th.emplace_back(part, n * t / nt, n * (t + 1) / nt);
+    for (uint64_t t = 0; t < nt; ++t) th.emplace_back(fn, n * t / nt, n * (t + 1) / nt);
     for (auto& t : th) t.join();
+}
+
+void decode_keys(const uint64_t* keys, uint64_t n, uint32_t* doc, uint32_t* score) {
+    split_over_threads(n, [=](uint64_t a, uint64_t b) {
+        for (uint64_t i = a; i < b; ++i) {
+            doc[i] = key_doc(keys[i]);
+            score[i] = key_score(keys[i]);
+        }
+    });
+}
+
+void copy_u32(uint32_t* dst, const uint32_t* src, uint64_t n) {
+    split_over_threads(n, [=](uint64_t a, uint64_t b) { std::memcpy(dst + a, src + a, (b - a) * 4); });
 }
 
 void throw_bad_base(uint32_t query) {
@@ -1499,7 +1509,7 @@ bool exhaustive_pipelined(cobsgpu_index* ix, const Slot& src, const std::vector<
     if (off || per_q == 0 || ix->pages.empty()) return false;
     // the arrays handed out are page-locked (~0.7 s per GB the first time a slot grows to a
     // size): beyond a few GB per call the general path's pageable arrays are the better deal
-    if (static_cast<uint64_t>(ids.size()) * per_q * 8 > PINNED_RESULT_MAX) return false;
+    if (static_cast<uint64_t>(ids.size()) * per_q * 8 > ix->pinned_result_max) return false;
     // Sub-batch size: every pass costs a few launches of fixed latency, and the first pass and the
     // last copy overlap nothing -- so at least "pipe_kb" (32 MB) of results per copy, and at most
     // about eight sub-batches.  A batch that fits one pass and is too short to split is left to
@@ -1583,6 +1593,10 @@ void run_exhaustive(cobsgpu_index* ix, const Slot& src, const std::vector<uint32
     pl.cap = std::max<uint32_t>(ix->shard_real_docs, 1);
     pl.limit = limit;
     const uint64_t out_per_q = (limit ? std::min<uint64_t>(limit, pl.cap) : pl.cap) * 8;
+    // the whole batch, one kind of pass: the sub-batches append to ONE list in query order, which
+    // collect_batch then takes over as it is (no second copy of what may be gigabytes)
+    const bool join = res_pin != nullptr && (huge_ids.empty() || dense_ids.empty());
+    size_t joined = static_cast<size_t>(-1);
     for (int huge = 0; huge < 2; ++huge) {
         const std::vector<uint32_t>& list = huge ? huge_ids : dense_ids;
         if (list.empty()) continue;
@@ -1641,16 +1655,45 @@ void run_exhaustive(cobsgpu_index* ix, const Slot& src, const std::vector<uint32
                     CK(cudaStreamSynchronize(st));
                 }
             }
+            const uint64_t* off = reinterpret_cast<const uint64_t*>(work.h_out.as<char>() + work.out_off);
+            const uint64_t total = off[n];
+            if (join && joined != static_cast<size_t>(-1)) {
+                // a later sub-batch of a joined batch: append
+                HostList& J = (*lists)[joined];
+                const uint64_t base = J.off.back(), have = J.doc.size();
+                for (uint32_t i = 1; i <= n; ++i) J.off.push_back(base + off[i]);
+                J.doc.resize(have + total);
+                J.score.resize(have + total);
+                if (total) {
+                    work.h_out.ensure(work.out_keys + total * 8);
+                    {
+                        PhaseScope ps(ix, PH_D2H, st);
+                        CK(cudaMemcpyAsync(work.h_out.as<char>() + work.out_keys, work.o_keys(), total * 8,
+                                           cudaMemcpyDeviceToHost, st));
+                    }
+                    CK(cudaStreamSynchronize(st));
+                    const char* got = work.h_out.as<char>() + work.out_keys;
+                    if (soa) {
+                        copy_u32(J.doc.data() + have, reinterpret_cast<const uint32_t*>(got), total);
+                        copy_u32(J.score.data() + have, reinterpret_cast<const uint32_t*>(got) + total, total);
+                    } else {
+                        decode_keys(reinterpret_cast<const uint64_t*>(got), total, J.doc.data() + have,
+                                    J.score.data() + have);
+                    }
+                }
+                for (size_t i = 0; i < n; ++i)
+                    (*where)[list[b + i]] = { static_cast<uint32_t>(joined), static_cast<uint32_t>(b + i) };
+                continue;
+            }
             lists->emplace_back();
             HostList& L = lists->back();
-            const uint64_t* off = reinterpret_cast<const uint64_t*>(work.h_out.as<char>() + work.out_off);
             L.off.assign(off, off + n + 1);
-            const uint64_t total = L.off[n];
+            if (join) joined = lists->size() - 1;
             // One pass that covers the whole batch and came out as doc[] | score[]: the arrays land
             // in the batch slot's own pinned buffer and are handed out as they are -- for lists of
             // every document of a large index, unpacking and copying cost more than the search.
             const bool hand_out = soa && res_pin != nullptr && sub >= list.size() && list.size() == ids.size() &&
-                                  total * 8 <= PINNED_RESULT_MAX;
+                                  total * 8 <= ix->pinned_result_max;
             if (hand_out && total) {
                 res_pin->ensure(total * 8);
                 {
@@ -1672,8 +1715,8 @@ void run_exhaustive(cobsgpu_index* ix, const Slot& src, const std::vector<uint32
                 CK(cudaStreamSynchronize(st));
                 const char* got = work.h_out.as<char>() + work.out_keys;
                 if (soa) {
-                    std::memcpy(L.doc.data(), got, total * 4);
-                    std::memcpy(L.score.data(), got + total * 4, total * 4);
+                    copy_u32(L.doc.data(), reinterpret_cast<const uint32_t*>(got), total);
+                    copy_u32(L.score.data(), reinterpret_cast<const uint32_t*>(got) + total, total);
                 } else {
                     decode_keys(reinterpret_cast<const uint64_t*>(got), total, L.doc.data(), L.score.data());
                 }
@@ -2680,6 +2723,7 @@ int cobsgpu_set_option(cobsgpu_index* ix, const char* name, int64_t value) {
         else if (n == "max_batch" && value >= 1) ix->max_batch = static_cast<uint32_t>(std::min<int64_t>(value, 1 << 22));
         else if (n == "workspace_mb" && value >= 1) ix->workspace_bytes = static_cast<uint64_t>(value) << 20;
         else if (n == "pipe_kb" && value >= 1) ix->pipe_bytes = static_cast<uint64_t>(value) << 10;
+        else if (n == "pinned_max_mb" && value >= 0) ix->pinned_result_max = static_cast<uint64_t>(value) << 20;
         else if (n == "timing") ix->timing = value != 0;
         else if (n == "prefetch") ix->prefetch = value != 0;
         else if (n == "inputs_ready") ix->inputs_ready = value != 0;

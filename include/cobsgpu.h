@@ -188,7 +188,9 @@ const char* cobsgpu_index_doc_name(const cobsgpu_index* idx, uint32_t doc);
  * default 1024), "max_batch" (queries per device batch, default 16384),
  * "workspace_mb" (bound for the exhaustive path, default 1024), "pipe_kb" (result KB per
  * device-to-host copy when lists of every document are returned in pipelined sub-batches,
- * default 32768), "timing" (0/1),
+ * default 32768), "pinned_max_mb" (lists of every document are handed out from page-locked
+ * memory up to this many MB per call, default 2048; larger results use pageable arrays),
+ * "timing" (0/1),
  * "prefetch" (0/1: cobsgpu_search_batch_device runs the metadata upload + K1 of a call on an
  * internal stream, double-buffered, so that they overlap the previous call's K2),
  * "inputs_ready" (0/1: with prefetch, the caller guarantees d_queries is already complete --

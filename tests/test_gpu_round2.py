@@ -259,6 +259,13 @@ def test_exhaustive_lists_in_pipelined_sub_batches(kind, n_docs, sig, h, ps):
         # a shorter batch next: the buffers of the previous call are reused
         for q, r, w in zip(qs[:5], g.search_batch(qs[:5], -1.0, 0), want[0]):
             assert as_list(r) == w, (pipe_kb, len(q))
+    # results beyond "pinned_max_mb": the general path (pageable arrays, sub-batch lists joined)
+    g.set_option("pinned_max_mb", 0)
+    g.set_option("workspace_mb", 1)
+    for q, r, w in zip(qs, g.search_batch(qs, 0.0, 0), want[0]):
+        assert as_list(r) == w, len(q)
+    g.set_option("pinned_max_mb", 2048)
+    g.set_option("workspace_mb", 1024)
     g.set_option("pipe_kb", 1)
     tickets = []
     for a, b in ((0, 4), (4, 11)):
