@@ -949,8 +949,18 @@ void launch_score(cobsgpu_index* ix, ScoreParams sp, int mode, bool lng, cudaStr
     sp.work = ix->d_work + 2 * (ix->work_slot++ % cobsgpu_index::WORK_RING);
     if (mode != MODE_KSPLIT) sp.n_kchunks = 1;
     const uint64_t items = static_cast<uint64_t>(sp.nq_items) * sp.n_tiles * sp.n_kchunks;
-    const uint32_t grid = static_cast<uint32_t>(
-        std::min<uint64_t>(items, static_cast<uint64_t>(cfg.occupancy) * ix->sm_count));
+    const uint64_t max_ctas = static_cast<uint64_t>(cfg.occupancy) * ix->sm_count;
+    uint64_t grid64 = std::min<uint64_t>(items, max_ctas);
+    // A few waves of long items (128 queries of 1000 k-mers on 7 tiles: 896 items for 444 CTAs):
+    // the last, nearly empty wave would run a handful of CTAs alone, each latency-bound
+    // (~0.18 us per k-mer) -- 0.18 of 0.84 ms there.  Fewer CTAs that all take the same number
+    // of items finish together; two CTAs per SM still keep > 100 KB of row data in flight.
+    static const bool no_balance = std::getenv("COBSGPU_NO_BALANCE") != nullptr;   // experiments only
+    if (!no_balance && items > max_ctas) {
+        const uint64_t waves = div_ceil<uint64_t>(items, max_ctas);
+        if (waves <= 16) grid64 = div_ceil<uint64_t>(items, waves);
+    }
+    const uint32_t grid = static_cast<uint32_t>(grid64);
     PhaseScope ps(ix, PH_SCORE, st);
     fn<<<grid, threads, cfg.smem, st>>>(sp);
     CK(cudaGetLastError());
