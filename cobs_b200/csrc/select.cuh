@@ -261,6 +261,43 @@ struct FinalizeParams {
 };
 
 static constexpr uint32_t FIN_SEL_UNROLL = 8;   // chunks of 32 candidates in flight per warp
+static constexpr uint32_t FIN_COOP_MAX_Q = 2;   // batches this small share the CTA's warps per query
+
+// Streaming selection for small limits (`-l 10`), one warp: returns the k smallest of
+// keys[begin, end) sorted over the lanes (lane i = i-th smallest, KEY_PAD where there are fewer;
+// lanes >= k hold larger keys or KEY_PAD).  A chunk of 32 candidates is tested against the
+// current k-th key with one ballot and only the few that beat it are inserted (expected
+// k * ln(n / k) insertions): no shared memory, no sort of the whole list.  FIN_SEL_UNROLL chunks
+// are loaded up front -- with one load per chunk the loop is a chain of L2 latencies, 77 of them
+// for the 2450 per-warp candidates of a single `-l 10` query on a million documents.
+__device__ __forceinline__ uint64_t select_stream(const uint64_t* keys, uint32_t begin, uint32_t end,
+                                                  uint32_t k, uint32_t lane) {
+    uint64_t best = KEY_PAD;
+    for (uint32_t base = begin; base < end; base += 32 * FIN_SEL_UNROLL) {
+        uint64_t chunk[FIN_SEL_UNROLL];
+#pragma unroll
+        for (uint32_t j = 0; j < FIN_SEL_UNROLL; ++j) {
+            const uint32_t i = base + j * 32 + lane;
+            chunk[j] = i < end ? keys[i] : KEY_PAD;
+        }
+#pragma unroll
+        for (uint32_t j = 0; j < FIN_SEL_UNROLL; ++j) {
+            const uint64_t key = chunk[j];
+            const uint64_t kth = __shfl_sync(0xFFFFFFFFu, best, k - 1);
+            uint32_t m = __ballot_sync(0xFFFFFFFFu, key < kth);
+            while (m) {
+                const uint32_t src = __ffs(m) - 1;
+                m &= m - 1;
+                const uint64_t x = __shfl_sync(0xFFFFFFFFu, key, src);
+                const uint32_t pos = __popc(__ballot_sync(0xFFFFFFFFu, best < x));
+                const uint64_t up = __shfl_up_sync(0xFFFFFFFFu, best, 1);
+                if (lane > pos) best = up;
+                else if (lane == pos) best = x;
+            }
+        }
+    }
+    return best;
+}
 
 __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(FinalizeParams p) {
     extern __shared__ __align__(16) uint64_t fin_s[];
@@ -269,6 +306,23 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(FinalizeParams
     const uint32_t q = blockIdx.x * FIN_WARPS + warp;
     const bool in_place = p.out_keys == p.cand;
     if (lane == 0) big_n[warp] = 0;
+    // One or two queries (the `cobs query <string>` pattern): a lone warp walking a query's
+    // candidates is most of K3's time, so every warp of the CTA first selects from its share of
+    // each query's list and the query's own warp then selects among those partial results.
+    __shared__ uint64_t coop_s[FIN_COOP_MAX_Q][FIN_WARPS * 32];
+    const bool coop = p.nq <= FIN_COOP_MAX_Q && p.limit != 0 && p.limit <= 32;   // uniform
+    if (coop) {
+        for (uint32_t cq = 0; cq < p.nq; ++cq) {
+            const uint32_t c = p.cand_count[cq];
+            const uint32_t n = c < p.cap ? c : p.cap;
+            const uint32_t per = ((n + FIN_WARPS - 1) / FIN_WARPS + 31) & ~31u;
+            const uint32_t b = warp * per < n ? warp * per : n;
+            const uint32_t e = b + per < n ? b + per : n;
+            coop_s[cq][warp * 32 + lane] = select_stream(p.cand + static_cast<uint64_t>(cq) * p.cap, b, e,
+                                                         static_cast<uint32_t>(p.limit), lane);
+        }
+        __syncthreads();
+    }
     if (q < p.nq) {
         const uint32_t c = p.cand_count[q];
         uint32_t n = c < p.cap ? c : p.cap;
@@ -280,39 +334,11 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(FinalizeParams
         if (lane == 0) p.out_counts[q] = invalid ? COUNT_INVALID : (over ? COUNT_OVERFLOW : r);
         if (over || invalid) n = 0;
         if (n > 32 && p.limit != 0 && p.limit <= 32) {
-            // Streaming selection for small limits (`-l 10`): `best` holds the k smallest keys
-            // seen so far, sorted over the lanes; a chunk of 32 candidates is tested against the
-            // current k-th key with one ballot and only the few that beat it are inserted
-            // (expected k * ln(n / k) insertions).  No shared memory, no sort of the whole list.
+            // the k best of a long list (the union of the per-warp top-k lists): streaming
+            // selection -- over the whole list, or over the partial selections of the CTA's warps
             const uint32_t k = static_cast<uint32_t>(p.limit);
-            const uint64_t* keys = p.cand + static_cast<uint64_t>(q) * p.cap;
-            uint64_t best = KEY_PAD;
-            // (FIN_SEL_UNROLL chunks are loaded up front: with one load per chunk the loop is a
-            // chain of L2 latencies -- 77 of them for the 2450 per-warp candidates of a single
-            // `-l 10` query on a million documents, most of that query's select time)
-            for (uint32_t base = 0; base < n; base += 32 * FIN_SEL_UNROLL) {
-                uint64_t chunk[FIN_SEL_UNROLL];
-#pragma unroll
-                for (uint32_t j = 0; j < FIN_SEL_UNROLL; ++j) {
-                    const uint32_t i = base + j * 32 + lane;
-                    chunk[j] = i < n ? keys[i] : KEY_PAD;
-                }
-#pragma unroll
-                for (uint32_t j = 0; j < FIN_SEL_UNROLL; ++j) {
-                    const uint64_t key = chunk[j];
-                    const uint64_t kth = __shfl_sync(0xFFFFFFFFu, best, k - 1);
-                    uint32_t m = __ballot_sync(0xFFFFFFFFu, key < kth);
-                    while (m) {
-                        const uint32_t src = __ffs(m) - 1;
-                        m &= m - 1;
-                        const uint64_t x = __shfl_sync(0xFFFFFFFFu, key, src);
-                        const uint32_t pos = __popc(__ballot_sync(0xFFFFFFFFu, best < x));
-                        const uint64_t up = __shfl_up_sync(0xFFFFFFFFu, best, 1);
-                        if (lane > pos) best = up;
-                        else if (lane == pos) best = x;
-                    }
-                }
-            }
+            const uint64_t best = coop ? select_stream(coop_s[q], 0, FIN_WARPS * 32, k, lane)
+                                       : select_stream(p.cand + static_cast<uint64_t>(q) * p.cap, 0, n, k, lane);
             if (lane < r) p.out_keys[static_cast<uint64_t>(q) * p.stride + lane] = best;
         } else if (n > 32) {
             if (lane == 0) big_n[warp] = n;

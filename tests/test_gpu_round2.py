@@ -51,6 +51,12 @@ def test_topk_epilogue_matches_oracle(kind, n_docs, sig, h, ps):
             got = g.search_batch(queries, thr, k)
             for q, r in zip(queries, got):
                 assert as_list(r) == oracle.search(o, q, thr, k), (thr, k, len(q))
+    # one or two queries per call (`cobs query <string>`): the warps of K3's CTA share each
+    # query's candidate list (partial selections + a final one) when the limit is at most 32
+    for k in (1, 7, 10, 32):
+        for sub in ([queries[0]], [queries[1]], queries[2:4], [queries[-2], queries[0]]):
+            for q, r in zip(sub, g.search_batch(sub, 0.0, k)):
+                assert as_list(r) == oracle.search(o, q, 0.0, k), ("small batch", k, len(q))
     g.close()
 
 
